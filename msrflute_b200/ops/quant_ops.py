@@ -1,0 +1,80 @@
+"""Segmented gradient quantization over a flat arena.
+
+``quantize_segments_`` = the reference transform (``extensions/quantization/quant.py:9-50``) applied per
+tensor segment.  CUDA path: ``csrc/quant_kernels.cu`` (segmented min/max/abs-quantile by 2-pass radix
+select on the float bit pattern, then a fused encode kernel).  ``pack_segments`` / ``unpack_add_`` are the
+real wire format: ``bits``-wide level codes + a 1-bit/elem keep mask + (lo, hi) per segment.
+"""
+from typing import Sequence, Tuple
+
+import torch
+
+from . import _ext
+
+
+def _seg_table(segments, device):
+    if torch.is_tensor(segments):
+        return segments.to(device=device, dtype=torch.int64).reshape(-1, 2)
+    return torch.tensor(list(segments), dtype=torch.int64, device=device).reshape(-1, 2)
+
+
+def segment_stats(flat: torch.Tensor, segments, quant_threshold: float, global_stats=False) -> torch.Tensor:
+    """``[n_seg, 3]`` (lo, hi, thresh) per segment."""
+    from ..extensions.quantization.quant import find_min_max_gradient
+    segs = segments.tolist() if torch.is_tensor(segments) else list(segments)
+    if global_stats:
+        allv = torch.cat([flat[o:o + n] for o, n in segs])
+        st = torch.stack(find_min_max_gradient(allv, quant_threshold))
+        return st.unsqueeze(0).expand(len(segs), 3).contiguous()
+    return torch.stack([torch.stack(find_min_max_gradient(flat[o:o + n], quant_threshold)) for o, n in segs])
+
+
+def quantize_segments_(flat: torch.Tensor, segments, quant_bits: int, quant_threshold: float, global_stats=False):
+    if _ext.use_cuda_kernels(flat) and not global_stats:
+        tab = _seg_table(segments, flat.device)
+        _ext.load().quantize_segments(flat, tab, int(quant_bits), float(quant_threshold))
+        _ext.count_launch(3)
+        return flat
+    from ..extensions.quantization.quant import quantize_tensor_
+    stats = segment_stats(flat, segments, quant_threshold, global_stats)
+    segs = segments.tolist() if torch.is_tensor(segments) else list(segments)
+    for i, (o, n) in enumerate(segs):
+        quantize_tensor_(flat[o:o + n], quant_bits, quant_threshold, tuple(stats[i]))
+    return flat
+
+
+def pack_segments(flat: torch.Tensor, segments, quant_bits: int, quant_threshold: float):
+    """Encode to (codes uint16/uint8, keep-mask uint8 bitmap, stats[n_seg,3]).  Lossless w.r.t.
+    :func:`quantize_segments_` — ``unpack`` reproduces exactly the simulated-quantization values."""
+    assert quant_bits <= 16
+    stats = segment_stats(flat, segments, quant_threshold)
+    segs = segments.tolist() if torch.is_tensor(segments) else list(segments)
+    n_bins = 2 ** quant_bits
+    code_dtype = torch.uint8 if quant_bits <= 8 else torch.int32
+    codes = torch.zeros(flat.numel(), dtype=code_dtype, device=flat.device)
+    keep = torch.zeros(flat.numel(), dtype=torch.bool, device=flat.device)
+    for i, (o, n) in enumerate(segs):
+        g = flat[o:o + n]
+        lo, hi, th = stats[i]
+        width = (hi - lo) / (n_bins - 1)
+        safe = torch.where(width > 0, width, torch.ones_like(width))
+        codes[o:o + n] = torch.ceil((g - lo) / safe - 0.5).clamp_(0, n_bins - 1).to(code_dtype)
+        keep[o:o + n] = g.abs() > th
+    pad = (-keep.numel()) % 8
+    kb = torch.cat([keep, keep.new_zeros(pad)]).view(-1, 8).to(torch.uint8)
+    bitmap = (kb * (2 ** torch.arange(8, device=flat.device, dtype=torch.uint8))).sum(dim=1).to(torch.uint8)
+    return codes, bitmap, stats
+
+
+def unpack_add_(out: torch.Tensor, codes, bitmap, stats, segments, quant_bits: int, alpha: float = 1.0):
+    """``out += alpha · dequant(codes, bitmap)`` — the decode half, fused with the server-side accumulation."""
+    segs = segments.tolist() if torch.is_tensor(segments) else list(segments)
+    n_bins = 2 ** quant_bits
+    bits = ((bitmap.unsqueeze(1) >> torch.arange(8, device=bitmap.device, dtype=torch.uint8)) & 1).bool().view(-1)
+    keep = bits[:out.numel()]
+    for i, (o, n) in enumerate(segs):
+        lo, hi, _ = stats[i]
+        width = (hi - lo) / (n_bins - 1)
+        vals = lo + codes[o:o + n].to(out.dtype) * width
+        out[o:o + n].add_(torch.where(keep[o:o + n], vals, torch.zeros_like(vals)), alpha=alpha)
+    return out
