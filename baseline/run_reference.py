@@ -1,0 +1,143 @@
+"""Reference arm of the benchmark: runs the UNMODIFIED microsoft/msrflute from ``baseline/_ref`` through its own
+entry point (``e2e_trainer.py`` ``__main__``: argparse → FLUTEConfig → ``run_worker`` → OptimizationServer /
+Worker) on synthetic Fed-CIFAR-100-shaped data, and times its FL rounds.
+
+Nothing of msrflute_b200 is on this path.  What is added around the reference:
+* ``baseline/shims``: offline stand-ins for the uninstallable imports (azureml, cerberus, easydict, h5py, wget);
+* the data files its own reader opens (``./data/fed_cifar100/*.h5``) pre-seeded with synthetic arrays;
+* a callback on the azureml shim that timestamps the reference's own per-round ``secsPerRoundTotal`` log call
+  (``core/server.py:499``) after a device synchronize — that is how rounds are delimited without touching its code.
+"""
+import json
+import os
+import runpy
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.path.join(HERE, "_ref")
+sys.path.insert(0, HERE)
+from bench_common import BASELINE_PUBLISHED_ROUNDS_PER_SEC, HEADLINE_METRIC, ClockSampler, emit, parse_args  # noqa: E402
+
+
+def seed_data(root):
+    import numpy as np
+    d = os.path.join(root, "data", "fed_cifar100")
+    os.makedirs(d, exist_ok=True)
+    tar = os.path.join(root, "data", "fed_cifar100.tar.bz2")
+    if not os.path.exists(tar):
+        open(tar, "wb").close()                       # its presence makes download_files() skip wget
+    for fname, users, seed in (("fed_cifar100_train.h5", 500, 5), ("fed_cifar100_test.h5", 100, 6)):
+        path = os.path.join(d, fname)
+        if os.path.exists(path):
+            continue
+        rng = np.random.default_rng(seed)
+        protos = rng.random((100, 32, 32, 3)).astype(np.float32)
+        n = 100
+        labels = rng.integers(0, 100, size=(users, n))
+        imgs = np.empty((users * n, 32, 32, 3), dtype=np.uint8)
+        for u in range(users):
+            x = 0.5 * protos[labels[u]] + 0.5 * rng.random((n, 32, 32, 3), dtype=np.float32)
+            imgs[u * n:(u + 1) * n] = (x * 255).astype(np.uint8)
+        with open(path, "wb") as f:
+            np.savez(f, users=np.array(["u{:05d}".format(u) for u in range(users)]),
+                     offsets=np.arange(users + 1) * n, f_image=imgs, f_label=labels.reshape(-1).astype(np.int64))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    os.environ.setdefault("RANK", str(rank))
+    os.environ.setdefault("WORLD_SIZE", str(world))
+    os.environ.setdefault("LOCAL_RANK", str(rank))
+    if not os.path.isdir(os.path.join(REF, "core")):
+        if rank == 0:
+            emit({"impl": "reference", "unavailable": "baseline/_ref missing: run baseline/install_reference.sh"})
+        return
+    os.chdir(REF)                                      # the reference resolves ./core/schema.py and ./experiments/…
+    sys.path[:0] = [os.path.join(HERE, "shims"), REF]
+    import torch
+    backend = os.environ.get("FLUTE_REF_BACKEND", "nccl")     # "gloo" = CPU smoke test of the shims only
+    if not torch.cuda.is_available() and backend != "gloo":
+        if rank == 0:
+            emit({"impl": "reference", "unavailable": "no CUDA device: the reference's NCCL path needs GPUs"})
+        return
+    if rank == 0:
+        seed_data(REF)
+    else:
+        while not os.path.exists(os.path.join(REF, "data", "fed_cifar100", "fed_cifar100_test.h5")):
+            time.sleep(0.5)
+        time.sleep(1.0)
+
+    import yaml
+    with open(os.path.join(REF, "experiments", args.task, "config.yaml")) as f:
+        cfg = yaml.safe_load(f)
+    total = args.warmup + args.steps
+    sc = cfg["server_config"]
+    sc["max_iteration"] = total
+    sc["num_clients_per_iteration"] = args.clients_per_round
+    sc["val_freq"], sc["rec_freq"] = 10 ** 9, 10 ** 9     # rounds only, like our arm: no eval inside the timed region
+    sc["initial_val"], sc["initial_rec"] = False, False
+    out_dir = os.path.join("/tmp", "flute_ref_bench_{}".format(os.environ.get("MASTER_PORT", "0")))
+    os.makedirs(out_dir, exist_ok=True)
+    cfg_path = os.path.join(out_dir, "bench_{}.yaml".format(args.task))
+    if rank == 0:
+        with open(cfg_path, "w") as f:
+            yaml.safe_dump(cfg, f)
+    else:
+        while not os.path.exists(cfg_path):
+            time.sleep(0.2)
+        time.sleep(0.5)
+
+    from azureml.core import Run
+    marks = []
+    state = {"sampler": None, "clocks": None}
+
+    def on_log(key, value):
+        if key != "secsPerRoundTotal":
+            return
+        ev = None
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            ev.synchronize()
+        marks.append((time.perf_counter(), ev))
+        if len(marks) == args.warmup:
+            state["sampler"] = ClockSampler(int(os.environ.get("LOCAL_RANK", 0))).start()
+        if len(marks) == total and state["sampler"] is not None:
+            state["clocks"] = state["sampler"].stop()
+
+    if rank == 0:
+        Run.get_context().callbacks.append(on_log)
+    sys.argv = ["e2e_trainer.py", "-dataPath", os.path.join(REF, "data"), "-outputPath", out_dir, "-config", cfg_path,
+                "-task", args.task, "-backend", backend]
+    t0 = time.perf_counter()
+    runpy.run_path(os.path.join(REF, "e2e_trainer.py"), run_name="__main__")
+    if rank != 0:
+        return
+    if len(marks) < total or args.warmup < 1:
+        emit({"impl": "reference", "unavailable": "reference finished {} of {} rounds".format(len(marks), total)})
+        return
+    (w0, e0), (w1, e1) = marks[args.warmup - 1], marks[total - 1]
+    wall_ms = (w1 - w0) * 1e3
+    ms = e0.elapsed_time(e1) if e0 is not None else wall_ms      # CUDA events on rank 0 (it waits for every worker)
+    value = args.steps / (ms / 1e3)
+    emit({"impl": "reference", "metric": HEADLINE_METRIC, "value": value, "unit": "rounds/s", "n_gpus": world,
+          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
+          "higher_is_better": True, "scaling": "strong", "vs_baseline": value / BASELINE_PUBLISHED_ROUNDS_PER_SEC,
+          "dtype": "fp32(tf32 conv)", "data": "synthetic Fed-CIFAR-100 shape (500 users x 100 x 32x32x3 uint8), random-init weights",
+          "clocks": state["clocks"],
+          "config": {"model": "reference RESNET as shipped (resnet18, BatchNorm2d, 1000-way FC)",
+                     "clients_per_round": args.clients_per_round, "client_batch": 20, "local_steps_per_client": 5,
+                     "global_batch": args.clients_per_round * 100, "seq_len": None,
+                     "parallelism": "server+{}workers".format(max(world - 1, 1)) if world > 1 else "single-gpu thread path",
+                     "l2": "inputs re-sampled every round; per-round working set (10 model replicas' traffic) > L2",
+                     "total_s_incl_startup": time.perf_counter() - t0}})
+
+
+if __name__ == "__main__":
+    main()

@@ -274,6 +274,7 @@ class Worker:
         self._acc = None         # Σ weight·pseudo-gradient over this rank's clients (fused mode)
         self._weights_list = None
         self.engine = None       # optional device-resident multi-client engine (core/engine.py)
+        self.round_events = []   # CUDA events recorded after every TRAIN command (device-side round timing)
 
     # ---- weight / accumulator buffers -------------------------------------
     def _arena(self):
@@ -396,12 +397,24 @@ class Worker:
                 else:
                     for o in outs:
                         _send_gradients((o.get("pl") or {}).get("gradients") or [], 0)
+                if torch.cuda.is_available():
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record()
+                    self.round_events.append(ev)
             elif cmd == COMMAND_TESTVAL:
                 comm.gather_objects(self.eval_clients(mine, ctrl["mode"], (0.0, None, 0)))
             elif cmd == COMMAND_SYNC_NODES:
                 comm.barrier()
             else:
                 raise AssertionError("unknown command {}".format(cmd))
+
+    def timed_region_ms(self, warmup, steps):
+        """Device time this rank spent between the end of round ``warmup`` and the end of round ``warmup+steps``."""
+        ev = self.round_events
+        if len(ev) < warmup + steps or warmup < 1:
+            return 0.0
+        ev[warmup + steps - 1].synchronize()
+        return float(ev[warmup - 1].elapsed_time(ev[warmup + steps - 1]))
 
     # ---- reference single-process entry points ------------------------------------------
     def trigger_train(self, lr, model_params, nround, client_idx):

@@ -86,6 +86,8 @@ B200_KEYS = {
     "server_is_worker": _opt("boolean", default=True),
     "dispatch": _opt("string", allowed=["static_lpt", "round_robin", "dynamic"], default="static_lpt"),
     "seed": _opt("integer", default=0),
+    "async_checkpoint": _opt("boolean"),
+    "device_engine": _opt("boolean", default=True),
 }
 
 

@@ -123,6 +123,9 @@ class OptimizationServer(federated.Server):
         if hasattr(self.strategy, "run_validation"):
             self.strategy.run_validation = self._validation_for_strategy
         self.round_hooks = []          # callables(round_idx, metrics_payload) — used by bench.py for timing
+        from . import trainer as _trainer_mod
+        _trainer_mod.ASYNC_CHECKPOINTS["enabled"] = bool(
+            server_config.get("b200", {}).get("async_checkpoint", torch.cuda.is_available()))
         print_rank(f"Server successfully instantiated strategy {self.strategy}", loglevel=logging.DEBUG)
 
     # ------------------------------------------------------------------ resume
@@ -174,33 +177,48 @@ class OptimizationServer(federated.Server):
 
     # -------------------------------------------------------------------- train
     def train(self):
+        try:
+            self.begin_training()
+            self.run_rounds(self.max_iteration - self.cur_iter_no)
+        finally:
+            self.end_training()
+
+    # The three phases of ``train`` are public so callers (bench.py, notebooks) can step rounds themselves.
+    def begin_training(self):
+        """Initial evaluation + the initial checkpoint dump (ref. ``server.py:232-255``)."""
         self.run_stats = {k: [] for k in (
             "secsPerClientRound", "secsPerClient", "secsPerClientTraining", "secsPerClientSetup",
             "secsPerClientFull", "secsPerRoundHousekeeping", "secsPerRoundTotal", "communicationCosts")}
         run.log("Max iterations", self.max_iteration)
-        try:
-            self.worker_trainer.model = to_device(self.worker_trainer.model)
-            eval_list = []
-            if self.cur_iter_no == 0:
-                if self.config["server_config"]["initial_rec"]:
-                    eval_list.append("test")
-                if self.config["server_config"]["initial_val"]:
-                    eval_list.append("val")
-                    run.log("LR for agg. opt.", get_lr(self.worker_trainer.optimizer))
-                print_rank("Running {} at itr={}".format(eval_list, self.cur_iter_no))
-                if eval_list:
-                    self.metrics = self.evaluation.run(eval_list, self.metrics, metric_logger=run.log)
-                eval_list = []
-            print_rank("Saving Model Before Starting Training", loglevel=logging.INFO)
-            for token in ["best_val_loss", "best_val_acc", "best_test_acc", "latest"]:
-                self.worker_trainer.save(model_path=self.model_path, token=token, config=self.config["server_config"])
+        self.worker_trainer.model = to_device(self.worker_trainer.model)
+        eval_list = []
+        if self.cur_iter_no == 0:
+            if self.config["server_config"]["initial_rec"]:
+                eval_list.append("test")
+            if self.config["server_config"]["initial_val"]:
+                eval_list.append("val")
+                run.log("LR for agg. opt.", get_lr(self.worker_trainer.optimizer))
+            print_rank("Running {} at itr={}".format(eval_list, self.cur_iter_no))
+            if eval_list:
+                self.metrics = self.evaluation.run(eval_list, self.metrics, metric_logger=run.log)
+        print_rank("Saving Model Before Starting Training", loglevel=logging.INFO)
+        for token in ["best_val_loss", "best_val_acc", "best_test_acc", "latest"]:
+            self.worker_trainer.save(model_path=self.model_path, token=token, config=self.config["server_config"])
+        self.worker_trainer.model.train()
 
-            self.worker_trainer.model.train()
-            for i in range(self.cur_iter_no, self.max_iteration):
-                self._train_round(i, eval_list)
-                eval_list = []
-        finally:
-            self.terminate_workers(terminate=(not self.do_clustering))
+    def run_rounds(self, n):
+        """Run ``n`` federated rounds starting at ``self.cur_iter_no``; returns the last round's train loss."""
+        last = None
+        for i in range(self.cur_iter_no, min(self.cur_iter_no + n, self.max_iteration)):
+            self._train_round(i, [])
+            self.cur_iter_no = i + 1
+            last = sum(self.train_loss) if self.train_loss else None
+        return last
+
+    def end_training(self):
+        from ..utils.async_ckpt import flush_checkpoints
+        flush_checkpoints()
+        self.terminate_workers(terminate=(not self.do_clustering))
 
     def _train_round(self, i, eval_list):
         begin = time.time()
@@ -289,8 +307,11 @@ class OptimizationServer(federated.Server):
             self.run_stats["secsPerClientSetup"][-1].append(client_stats["setup"])
             self.run_stats["secsPerClient"][-1].append(client_end - clients_begin)
 
+        fused_done = False
         if fused:
-            self._install_fused_aggregate(fused_weights)
+            fused_done = self._fused_server_update(fused_weights, i, num_clients_curr_iter, log_metric)
+            if not fused_done:
+                self._install_fused_aggregate(fused_weights)
 
         if self.do_profiling:
             profiler.disable()
@@ -315,9 +336,10 @@ class OptimizationServer(federated.Server):
         begin = end
         log_metric("Training loss", sum(self.train_loss))
 
-        self.losses = self.strategy.combine_payloads(
-            worker_trainer=self.worker_trainer, curr_iter=i, num_clients_curr_iter=num_clients_curr_iter,
-            total_clients=len(self.client_idx_list), client_stats=client_stats, logger=log_metric)
+        if not fused_done:
+            self.losses = self.strategy.combine_payloads(
+                worker_trainer=self.worker_trainer, curr_iter=i, num_clients_curr_iter=num_clients_curr_iter,
+                total_clients=len(self.client_idx_list), client_stats=client_stats, logger=log_metric)
 
         if self.server_trainer is not None:
             print_rank("Running replay iterations on server")
@@ -353,6 +375,9 @@ class OptimizationServer(federated.Server):
                     print_rank("LOG: Client weight of learning rate {}..".format(self.lr_weight))
 
         self.backup_models(i)
+        if (i % self.model_backup_freq) == 0:
+            from ..utils.async_ckpt import flush_checkpoints
+            flush_checkpoints()         # the epoch<i>_best_* copies below read files back
         self.fall_back_to_prev_best_status()
         if len(self.metrics) > 1:
             update_json_log(self.log_path, {
@@ -385,6 +410,44 @@ class OptimizationServer(federated.Server):
             run.log(k, v)
         for hook in self.round_hooks:
             hook(i, metrics_payload)
+
+    def _fused_server_update(self, weights, curr_iter, num_clients_curr_iter, log_metric):
+        """Fast path: the weighted pseudo-gradient sums (already reduced onto this rank, or peer-mapped when the
+        transport is symmetric memory) go through ONE fused reduce/normalise/DP/optimizer/broadcast kernel
+        (``ModelUpdater.fused_update``).  Returns False when some option needs the generic strategy path."""
+        if not torch.cuda.is_available() or not weights or self.strategy.skip_model_update:
+            return False
+        if self.config.get("dump_norm_stats", False):
+            return False
+        worker = self.single_worker or federated._Runtime.worker
+        comm = federated.get_comm()
+        dp = self.config.get("dp_config", None) or {}
+        noise_scale, seed, stats_out = 0.0, 0, None
+        is_dga = type(self.strategy).__name__ == "DGA"
+        if is_dga and dp.get("enable_global_dp", False):
+            assert dp["enable_local_dp"], "global DP requires enable_local_dp (client-side clipping)"
+            noise_scale = dp["global_sigma"] * dp["max_grad"] / num_clients_curr_iter
+            seed = (int(self.config["server_config"].get("b200", {}).get("seed", 0)) << 32) ^ (curr_iter + 1)
+            stats_out = torch.zeros(2, device=worker.accumulator().device)
+        wsum = torch.tensor(float(sum(weights)), device=worker.accumulator().device)
+        accs = comm.peer_accumulators(worker.accumulator()) if hasattr(comm, "peer_accumulators") \
+            else [worker.accumulator()]
+        bcast = comm.peer_weight_buffers(worker.weight_buffer()) if hasattr(comm, "peer_weight_buffers") else None
+        ok = self.worker_trainer.fused_update(accs, wsum, noise_scale=noise_scale, seed=seed, bcast=bcast,
+                                              stats_out=stats_out)
+        if not ok:
+            return False
+        if bcast is not None:
+            self._weights_in_sync = True
+        self.strategy.client_weights, self.strategy.client_parameters_stack = [], []
+        if stats_out is not None:
+            log_metric("Gradient Norm", float(stats_out[0].item()))
+        if is_dga:
+            from ..extensions import privacy
+            privacy.update_privacy_accountant(self.config, len(self.client_idx_list), curr_iter=curr_iter,
+                                              num_clients_curr_iter=num_clients_curr_iter, metric_logger=log_metric)
+        self.losses = self.worker_trainer.run_lr_scheduler(force_run_val=False)
+        return True
 
     def _install_fused_aggregate(self, weights):
         """Move Σ_ranks Σ_clients weight·pseudo-grad (already reduced onto this rank) into ``model.grad`` and tell

@@ -75,6 +75,8 @@ class TrainerBase:
 
     def load(self, save_path, update_lr_scheduler, update_ss_scheduler):
         """Restore model/optimizer(/schedulers) from ``save_path`` if it exists."""
+        from ..utils.async_ckpt import flush_checkpoints
+        flush_checkpoints()
         if not os.path.isfile(save_path):
             return False
         print_rank("Loading checkpoint: {}".format(save_path))
@@ -110,6 +112,72 @@ class ModelUpdater(TrainerBase):
             print_rank(f"clipped norm: {grad_norm} to {min(float(grad_norm), self.max_grad_norm)}", logging.DEBUG)
         self.optimizer.step()
         self.optimizer.zero_grad(set_to_none=False)
+
+    # ---- fused device path ---------------------------------------------
+    _FUSABLE = {"SGD": "sgd", "Adam": "adam", "AdamW": "adamW", "Adamax": "adamax", "LAMB": "lamb",
+                "LarsSGD": "LarsSGD"}
+
+    def fused_state(self):
+        """Build (once) the arena-resident optimizer state used by ``ops.arena_ops.server_update``; the torch
+        optimizer's ``state`` entries are re-pointed at views of those arenas so ``state_dict()`` checkpoints
+        stay in the reference's format."""
+        if getattr(self, "_fused", None) is not None:
+            return self._fused
+        opt = self.optimizer
+        ar = module_arena(self.model)
+        kind = self._FUSABLE.get(type(opt).__name__)
+        from ..utils.optimizers import AdamW as _OurAdamW
+        if ar is None or kind is None or len(opt.param_groups) != 1:
+            return None
+        if type(opt).__name__ == "AdamW" and not isinstance(opt, _OurAdamW):
+            return None                  # torch.optim.AdamW has different decay semantics
+        g = opt.param_groups[0]
+        if g.get("amsgrad", False) or g.get("maximize", False) or not next(self.model.parameters()).is_cuda:
+            return None
+        if len(opt.state) != 0:
+            return None                  # resumed state lives in per-tensor buffers; keep the torch path
+        w = ar[0]
+        st = arena_ops.ServerOptState(
+            kind, w.flat.numel(), w.flat.device, lr=g["lr"], betas=g.get("betas", (0.9, 0.999)),
+            eps=g.get("eps", 1e-8), weight_decay=g.get("weight_decay", 0.0) or 0.0, momentum=g.get("momentum", 0.0) or 0.0,
+            dampening=g.get("dampening", 0.0) or 0.0, nesterov=g.get("nesterov", False),
+            correct_bias=g.get("correct_bias", True))
+        lay = w.layout
+        mv = lay.views(st.m) if st.m is not None else None
+        vv = lay.views(st.v) if st.v is not None else None
+        for i, p in enumerate(self.model.parameters()):
+            s = opt.state[p]
+            if kind == "sgd":
+                if st.m is not None:
+                    s["momentum_buffer"] = mv[i]
+            elif kind == "LarsSGD":
+                if st.m is not None:
+                    s["momentum_buffer"] = mv[i]
+            else:
+                s["step"] = 0 if kind in ("adamW", "lamb") else torch.tensor(0.0)
+                s["exp_avg"] = mv[i]
+                s["exp_avg_sq" if kind != "adamax" else "exp_inf"] = vv[i]
+        self._fused = (st, lay.segments(w.flat.device))
+        return self._fused
+
+    def fused_update(self, accs, weight_sum, noise_scale=0.0, seed=0, bcast=None, stats_out=None, grad_out=None):
+        """One fused pass: Σ_ranks acc / Σw (+noise) (+clip) → optimizer → broadcast.  Returns False when the
+        configuration has no fused kernel (caller falls back to ``update_model``)."""
+        fs = self.fused_state()
+        if fs is None:
+            return False
+        st, segs = fs
+        g = self.optimizer.param_groups[0]
+        st.lr = float(g["lr"])
+        w = module_arena(self.model)[0].flat
+        arena_ops.server_update(w, accs, weight_sum, st, grad_out=grad_out, noise_scale=noise_scale, seed=seed,
+                                max_grad_norm=self.max_grad_norm, segments=segs, bcast=bcast, zero_accs=True,
+                                stats_out=stats_out)
+        for p in self.model.parameters():          # keep the per-parameter step counters in sync for checkpoints
+            s = self.optimizer.state.get(p)
+            if s is not None and "step" in s:
+                s["step"] = st.step if not torch.is_tensor(s["step"]) else torch.tensor(float(st.step))
+        return True
 
     def run_lr_scheduler(self, force_run_val=False):
         val_loss = val_acc = None
@@ -450,6 +518,10 @@ class Trainer(TrainerBase):
             self.lr_scheduler = make_lr_scheduler(annealing_config, self.optimizer)
 
 
+#: set by the server from ``server_config.b200.async_checkpoint`` (default: on when CUDA is available)
+ASYNC_CHECKPOINTS = {"enabled": False}
+
+
 def run_validation_generic(model, val_dataloader):
     """Evaluate ``model`` on a loader; returns ``(outputs, metrics)`` (ref. ``trainer.py:690-723``)."""
     model.set_eval()
@@ -479,6 +551,10 @@ def save_model(model_path, config, model, optimizer, lr_scheduler, ss_scheduler,
         state["ss_scheduler_state_dict"] = ss_scheduler.state_dict()
     save_path = os.path.join(model_path, "{}_model.tar".format(token) if token else "model.tar")
     print_rank("Saving model to: {}".format(save_path), logging.DEBUG)
-    try_except_save(torch_save, state_or_model=state, save_path=save_path)
+    if ASYNC_CHECKPOINTS["enabled"]:
+        from ..utils.async_ckpt import get_checkpointer
+        get_checkpointer().submit(save_path, state)
+    else:
+        try_except_save(torch_save, state_or_model=state, save_path=save_path)
     if config is not None:
         try_except_save(write_yaml, config=config, save_path=os.path.join(model_path, "config.yaml"))

@@ -1,0 +1,255 @@
+// Flat-arena kernels for the client side of a federated round.
+//
+//   fused_client_step   : global-norm clip + gradient sufficient statistics + SGD(momentum, wd) + zero-grad
+//                         over [S rows x P] in two launches (reduce, then update) — replaces
+//                         clip_grad_norm_ + per-parameter grad.clone().cpu().numpy() + optimizer.step()
+//                         of the reference (core/trainer.py:383-391), for S simulated clients at once.
+//   clip_and_stats      : the first half only (non-SGD client optimizers).
+//   pseudo_grad         : out = (w_global - w_local) * weight  (+ sum / sum^2 of the raw pseudo-gradient).
+//   accumulate_pseudo_grad : acc += sum_s weight[s] * (w_global - w_local[s])  — the worker-side half of the
+//                         gather: weighting (fedavg.py:80) and aggregation (strategies/utils.py:21-33) in one pass.
+//
+// All buffers are fp32, rows are 128-byte aligned (parallel/arena.py) so every access is a 16-byte vector.
+// These kernels are HBM-bandwidth bound by construction (1 FMA per 4-16 bytes); the only design goals are
+// 16-byte coalesced streaming accesses, enough bytes in flight, and one pass over the data.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include "common.cuh"
+
+namespace flute {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;  // float4 per thread per iteration -> 64 B in flight per thread
+
+static inline int blocks_for(int64_t n_vec4) {
+  // persistent-ish sizing: at most 2 CTAs per SM (148 SMs), at least 1
+  int64_t want = (n_vec4 + kThreads * kUnroll - 1) / (kThreads * kUnroll);
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, 148 * 2)));
+}
+
+// ---------------------------------------------------------------------------------------------------- reduce
+// partial[s][b] = (sum g, sum g^2) over block b's share of row s
+__global__ void __launch_bounds__(kThreads) row_reduce_kernel(const float* __restrict__ g, int64_t P,
+                                                              float2* __restrict__ partial) {
+  const int s = blockIdx.y;
+  const float4* gv = reinterpret_cast<const float4*>(g + static_cast<int64_t>(s) * P);
+  const int64_t n4 = P >> 2;
+  float a = 0.f, b = 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  for (; i + (kUnroll - 1) * stride < n4; i += kUnroll * stride) {
+    float4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) v[u] = ld_na(gv + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      a += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+      b += (v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w);
+    }
+  }
+  for (; i < n4; i += stride) {
+    const float4 v = ld_na(gv + i);
+    a += (v.x + v.y) + (v.z + v.w);
+    b += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  const float2 r = block_sum2(a, b);
+  if (threadIdx.x == 0) partial[static_cast<int64_t>(s) * gridDim.x + blockIdx.x] = r;
+}
+
+__device__ __forceinline__ float2 fold_partials(const float2* __restrict__ partial, int nb) {
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    const float2 p = partial[i];
+    a += p.x;
+    b += p.y;
+  }
+  return block_sum2(a, b);
+}
+
+// ---------------------------------------------------------------------------------------------------- update
+// hyper row: lr, max_norm, wd, momentum.  stats row: sum, sumsq, count, last_norm.
+template <bool kMomentum, bool kStepOnly>
+__global__ void __launch_bounds__(kThreads)
+row_update_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ mom, int64_t P,
+                  const float2* __restrict__ partial, int nb_reduce, const float* __restrict__ hyper,
+                  float* __restrict__ stats, const int* __restrict__ first_step, float n_logical, bool nesterov,
+                  float dampening, bool zero_grad) {
+  const int s = blockIdx.y;
+  const float2 tot = fold_partials(partial + static_cast<int64_t>(s) * nb_reduce, nb_reduce);
+  const float lr = hyper[s * 4 + 0], max_norm = hyper[s * 4 + 1], wd = hyper[s * 4 + 2], mu = hyper[s * 4 + 3];
+  const float norm = sqrtf(tot.y);
+  const float coef = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    stats[s * 4 + 0] += coef * tot.x;
+    stats[s * 4 + 1] += coef * coef * tot.y;
+    stats[s * 4 + 2] += n_logical;
+    stats[s * 4 + 3] = norm;
+  }
+  const bool first = kMomentum && first_step != nullptr && first_step[s] != 0;
+  float4* wv = reinterpret_cast<float4*>(w + static_cast<int64_t>(s) * P);
+  float4* gv = reinterpret_cast<float4*>(g + static_cast<int64_t>(s) * P);
+  float4* mv = kMomentum ? reinterpret_cast<float4*>(mom + static_cast<int64_t>(s) * P) : nullptr;
+  const int64_t n4 = P >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n4; i += stride) {
+    float4 gg = ld_na(gv + i);
+    if (kStepOnly) {  // clip_and_stats: scale the gradient in place, nothing else
+      gg.x *= coef; gg.y *= coef; gg.z *= coef; gg.w *= coef;
+      st_stream(gv + i, gg);
+      continue;
+    }
+    float4 ww = ld_na(wv + i);
+    float4 d = make_float4(fmaf(coef, gg.x, wd * ww.x), fmaf(coef, gg.y, wd * ww.y), fmaf(coef, gg.z, wd * ww.z),
+                           fmaf(coef, gg.w, wd * ww.w));
+    if (kMomentum) {
+      float4 m = ld_na(mv + i);
+      if (first) {
+        m = d;
+      } else {
+        const float k = 1.f - dampening;
+        m = make_float4(fmaf(mu, m.x, k * d.x), fmaf(mu, m.y, k * d.y), fmaf(mu, m.z, k * d.z), fmaf(mu, m.w, k * d.w));
+      }
+      st_stream(mv + i, m);
+      d = nesterov ? make_float4(fmaf(mu, m.x, d.x), fmaf(mu, m.y, d.y), fmaf(mu, m.z, d.z), fmaf(mu, m.w, d.w)) : m;
+    }
+    ww.x = fmaf(-lr, d.x, ww.x); ww.y = fmaf(-lr, d.y, ww.y); ww.z = fmaf(-lr, d.z, ww.z); ww.w = fmaf(-lr, d.w, ww.w);
+    st_stream(wv + i, ww);
+    if (zero_grad) st_stream(gv + i, zero);
+  }
+}
+
+static void check_rows(const torch::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kFloat32 && t.dim() == 2 && t.is_contiguous(), name,
+              " must be a contiguous fp32 CUDA [S, P] tensor");
+  TORCH_CHECK(t.size(1) % 4 == 0, name, ": row length must be a multiple of 4 floats (arena padding)");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0, name, " must be 16-byte aligned");
+}
+
+void fused_client_step(torch::Tensor w, torch::Tensor g, torch::Tensor hyper, torch::Tensor stats,
+                       c10::optional<torch::Tensor> mom, c10::optional<torch::Tensor> first_step, int64_t n_logical,
+                       bool nesterov, double dampening, bool zero_grad) {
+  check_rows(w, "w");
+  check_rows(g, "g");
+  TORCH_CHECK(w.sizes() == g.sizes(), "w/g shape mismatch");
+  const int S = static_cast<int>(w.size(0));
+  const int64_t P = w.size(1);
+  TORCH_CHECK(hyper.is_cuda() && hyper.numel() == S * 4 && stats.is_cuda() && stats.numel() == S * 4);
+  const c10::cuda::CUDAGuard guard(w.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int nb = blocks_for(P >> 2);
+  auto partial = torch::empty({S, nb, 2}, w.options());
+  row_reduce_kernel<<<dim3(nb, S), kThreads, 0, stream>>>(g.data_ptr<float>(), P,
+                                                         reinterpret_cast<float2*>(partial.data_ptr<float>()));
+  const int* fs = first_step.has_value() ? first_step->data_ptr<int>() : nullptr;
+  if (mom.has_value()) {
+    check_rows(*mom, "mom");
+    row_update_kernel<true, false><<<dim3(nb, S), kThreads, 0, stream>>>(
+        w.data_ptr<float>(), g.data_ptr<float>(), mom->data_ptr<float>(), P,
+        reinterpret_cast<const float2*>(partial.data_ptr<float>()), nb, hyper.data_ptr<float>(), stats.data_ptr<float>(),
+        fs, static_cast<float>(n_logical), nesterov, static_cast<float>(dampening), zero_grad);
+  } else {
+    row_update_kernel<false, false><<<dim3(nb, S), kThreads, 0, stream>>>(
+        w.data_ptr<float>(), g.data_ptr<float>(), nullptr, P, reinterpret_cast<const float2*>(partial.data_ptr<float>()),
+        nb, hyper.data_ptr<float>(), stats.data_ptr<float>(), nullptr, static_cast<float>(n_logical), nesterov,
+        static_cast<float>(dampening), zero_grad);
+  }
+  FLUTE_CUDA_CHECK(cudaGetLastError());
+}
+
+void clip_and_stats(torch::Tensor g, torch::Tensor hyper, torch::Tensor stats, int64_t n_logical) {
+  check_rows(g, "g");
+  const int S = static_cast<int>(g.size(0));
+  const int64_t P = g.size(1);
+  const c10::cuda::CUDAGuard guard(g.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int nb = blocks_for(P >> 2);
+  auto partial = torch::empty({S, nb, 2}, g.options());
+  row_reduce_kernel<<<dim3(nb, S), kThreads, 0, stream>>>(g.data_ptr<float>(), P,
+                                                         reinterpret_cast<float2*>(partial.data_ptr<float>()));
+  row_update_kernel<false, true><<<dim3(nb, S), kThreads, 0, stream>>>(
+      nullptr, g.data_ptr<float>(), nullptr, P, reinterpret_cast<const float2*>(partial.data_ptr<float>()), nb,
+      hyper.data_ptr<float>(), stats.data_ptr<float>(), nullptr, static_cast<float>(n_logical), false, 0.f, false);
+  FLUTE_CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ pseudo-grad
+__global__ void __launch_bounds__(kThreads)
+pseudo_grad_kernel(const float* __restrict__ wg, const float* __restrict__ wl, float* __restrict__ out, int64_t P,
+                   const float* __restrict__ weight, float* __restrict__ stats) {
+  const float wt = weight != nullptr ? *weight : 1.f;
+  const float4* a = reinterpret_cast<const float4*>(wg);
+  const float4* b = reinterpret_cast<const float4*>(wl);
+  float4* o = reinterpret_cast<float4*>(out);
+  const int64_t n4 = P >> 2, stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n4; i += stride) {
+    const float4 x = ld_stream(a + i), y = ld_na(b + i);
+    const float4 d = make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w);
+    s1 += (d.x + d.y) + (d.z + d.w);
+    s2 += (d.x * d.x + d.y * d.y) + (d.z * d.z + d.w * d.w);
+    st_stream(o + i, make_float4(d.x * wt, d.y * wt, d.z * wt, d.w * wt));
+  }
+  if (stats != nullptr) {
+    const float2 r = block_sum2(s1, s2);
+    if (threadIdx.x == 0) {
+      atomicAdd(stats + 0, r.x);
+      atomicAdd(stats + 1, r.y);
+    }
+  }
+}
+
+void pseudo_grad(torch::Tensor wg, torch::Tensor wl, torch::Tensor out, c10::optional<torch::Tensor> weight,
+                 c10::optional<torch::Tensor> stats) {
+  TORCH_CHECK(wg.is_cuda() && wg.scalar_type() == torch::kFloat32 && wg.numel() == wl.numel() && wg.numel() == out.numel());
+  TORCH_CHECK(wg.numel() % 4 == 0, "arena length must be a multiple of 4");
+  const c10::cuda::CUDAGuard guard(wg.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  if (stats.has_value()) stats->narrow(0, 0, 2).zero_();
+  const int64_t P = wg.numel();
+  pseudo_grad_kernel<<<blocks_for(P >> 2), kThreads, 0, stream>>>(
+      wg.data_ptr<float>(), wl.data_ptr<float>(), out.data_ptr<float>(), P,
+      weight.has_value() ? weight->data_ptr<float>() : nullptr, stats.has_value() ? stats->data_ptr<float>() : nullptr);
+  FLUTE_CUDA_CHECK(cudaGetLastError());
+}
+
+// acc[i] += sum_s wts[s] * active[s] * (wg[i] - wl[s][i])
+__global__ void __launch_bounds__(kThreads)
+accumulate_pg_kernel(float* __restrict__ acc, const float* __restrict__ wg, const float* __restrict__ wl, int64_t P,
+                     int S, const float* __restrict__ wts, const int* __restrict__ active) {
+  extern __shared__ float s_w[];
+  for (int s = threadIdx.x; s < S; s += blockDim.x) s_w[s] = (active == nullptr || active[s] != 0) ? wts[s] : 0.f;
+  __syncthreads();
+  const int64_t n4 = P >> 2, stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  const float4* g4 = reinterpret_cast<const float4*>(wg);
+  float4* a4 = reinterpret_cast<float4*>(acc);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n4; i += stride) {
+    const float4 x = ld_stream(g4 + i);
+    float4 r = ld_na(a4 + i);
+    for (int s = 0; s < S; ++s) {
+      const float wt = s_w[s];
+      if (wt == 0.f) continue;
+      const float4 y = ld_stream(reinterpret_cast<const float4*>(wl + static_cast<int64_t>(s) * P) + i);
+      r.x = fmaf(wt, x.x - y.x, r.x); r.y = fmaf(wt, x.y - y.y, r.y);
+      r.z = fmaf(wt, x.z - y.z, r.z); r.w = fmaf(wt, x.w - y.w, r.w);
+    }
+    st_stream(a4 + i, r);
+  }
+}
+
+void accumulate_pseudo_grad(torch::Tensor acc, torch::Tensor wg, torch::Tensor wl, torch::Tensor weights,
+                            c10::optional<torch::Tensor> active) {
+  check_rows(wl, "w_local");
+  const int S = static_cast<int>(wl.size(0));
+  const int64_t P = wl.size(1);
+  TORCH_CHECK(acc.numel() == P && wg.numel() == P && weights.numel() == S && weights.scalar_type() == torch::kFloat32);
+  const c10::cuda::CUDAGuard guard(acc.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  accumulate_pg_kernel<<<blocks_for(P >> 2), kThreads, S * sizeof(float), stream>>>(
+      acc.data_ptr<float>(), wg.data_ptr<float>(), wl.data_ptr<float>(), P, S, weights.data_ptr<float>(),
+      active.has_value() ? active->data_ptr<int>() : nullptr);
+  FLUTE_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace flute

@@ -1,0 +1,351 @@
+// bf16 GEMM on the 5th-generation tensor cores: C[g] = A[g] (M x K) * B[g]^T (N x K)  (+bias, +ReLU)
+//
+// Both operands are K-major ("TN"), the layout every Linear / conv-as-GEMM / LSTM projection in this framework
+// produces.  Structure (one 128 x BLOCK_N output tile per CTA, 192 threads):
+//
+//   warp 0      TMA producer  : cp.async.bulk.tensor.3d (global -> 128B-swizzled smem), 4-stage mbarrier ring
+//   warp 1      MMA issuer    : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BLOCK_N x 16),
+//                               fp32 accumulator in TMEM; tcgen05.commit releases smem stages / signals the epilogue
+//   warps 2..5  epilogue      : tcgen05.ld 32x32b (TMEM -> registers), + bias, ReLU, convert, 16-byte global stores
+//
+// M/N/K tails are handled by TMA out-of-bounds zero fill and store predication.  Batched via grid.z (3-D tensor maps).
+// No CUTLASS: descriptors and PTX are spelled out below (layouts follow the PTX ISA "tcgen05 matrix descriptors").
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include "common.cuh"
+
+namespace flute {
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;            // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(smem_result)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 columns of 32-bit: thread t of the warp receives lane (base_lane + t), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ descriptors
+// Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B: rows are 128 B, 8-row groups are 1024 B apart.
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major) |
+//   [32,46) stride byte offset >> 4 (= 1024 >> 4) | [46,48) descriptor version = 1 | [61,64) layout type (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: [4,6) D format (1 = f32) | [7,10) A format (1 = bf16) | [10,13) B format (1 = bf16) |
+//   bit 15 / 16: A / B major (0 = K-major) | [17,23) N >> 3 | [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(umma_n >> 3) << 17) |
+         (static_cast<uint32_t>(umma_m >> 4) << 24);
+}
+
+struct EpilogueParams {
+  void* C;              // [G, M, N] bf16 or fp32, row-major
+  const float* bias;    // [N] or nullptr
+  int M, N, K;
+  long long c_batch_stride;
+  int relu;
+  int out_fp32;
+};
+
+template <int BLOCK_N>
+struct SmemLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const EpilogueParams ep) {
+  using L = SmemLayout<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.x, n_blk = blockIdx.y, g = blockIdx.z;
+  const int num_k_blocks = (ep.K + BLOCK_K - 1) / BLOCK_K;
+  constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;      // power of two >= 32
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t phase = (kb / kStages) & 1;
+        mbar_wait(empty_bar + s, phase ^ 1);
+        uint8_t* sa = smem + s * L::kStageBytes;
+        uint8_t* sb = sa + L::kABytes;
+        mbar_expect_tx(full_bar + s, L::kStageBytes);
+        tma_load_3d(sa, &map_a, full_bar + s, kb * BLOCK_K, m_blk * BLOCK_M, g);
+        tma_load_3d(sb, &map_b, full_bar + s, kb * BLOCK_K, n_blk * BLOCK_N, g);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (single elected lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t phase = (kb / kStages) & 1;
+        mbar_wait(full_bar + s, phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+        const uint32_t b_addr = a_addr + L::kABytes;
+        const uint64_t adesc = make_smem_desc(a_addr), bdesc = make_smem_desc(b_addr);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+          umma_f16(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                   (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar + s);                     // smem stage reusable once these MMAs retire
+      }
+      umma_commit(tmem_full_bar);                       // accumulator complete
+    }
+  } else {
+    // ===================================================== epilogue: TMEM -> registers -> global
+    const int q = warp & 3;                             // TMEM lane quadrant this warp may access
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = m_blk * BLOCK_M + q * 32 + lane;
+    const long long c_off = static_cast<long long>(g) * ep.c_batch_stride + static_cast<long long>(row) * ep.N;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), v);
+      const int col0 = n_blk * BLOCK_N + c0;
+      if (row < ep.M && col0 < ep.N) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]);
+          if (ep.bias != nullptr && col0 + j < ep.N) x += ep.bias[col0 + j];
+          if (ep.relu) x = fmaxf(x, 0.f);
+          f[j] = x;
+        }
+        const bool full = (col0 + 32 <= ep.N);
+        if (ep.out_fp32) {
+          float* dst = reinterpret_cast<float*>(ep.C) + c_off + col0;
+          if (full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            for (int j = 0; j < 32 && col0 + j < ep.N; ++j) dst[j] = f[j];
+          }
+        } else {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.C) + c_off + col0;
+          if (full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+              pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+              *reinterpret_cast<uint4*>(dst + j) = pk;
+            }
+          } else {
+            for (int j = 0; j < 32 && col0 + j < ep.N; ++j) dst[j] = __float2bfloat16(f[j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    cudaDriverEntryPointQueryResult qres;
+    void* p = nullptr;
+    FLUTE_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    TORCH_CHECK(qres == cudaDriverEntryPointSuccess && p != nullptr, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// 3-D map over a [G, R, K] bf16 row-major tensor; box = [1, box_rows, BLOCK_K], 128-byte swizzle, zero OOB fill.
+static CUtensorMap make_map(const void* ptr, int64_t G, int64_t R, int64_t K, int64_t batch_stride_elems, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(R), static_cast<cuuint64_t>(G)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(K) * 2, static_cast<cuuint64_t>(batch_stride_elems) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TORCH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code ", static_cast<int>(r));
+  return m;
+}
+
+template <int BLOCK_N>
+static void launch(const CUtensorMap& ma, const CUtensorMap& mb, const EpilogueParams& ep, int G, cudaStream_t stream) {
+  using L = SmemLayout<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    FLUTE_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  dim3 grid((ep.M + BLOCK_M - 1) / BLOCK_M, (ep.N + BLOCK_N - 1) / BLOCK_N, G);
+  gemm_bf16_tn_kernel<BLOCK_N><<<grid, kThreads, L::kTotal, stream>>>(ma, mb, ep);
+  FLUTE_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace gemm
+
+// a: [M, K] or [G, M, K] bf16 ; b: [N, K] or [G, N, K] bf16 (a 2-D b is shared by all batches) -> C [.., M, N]
+torch::Tensor gemm_bf16_tn(torch::Tensor a, torch::Tensor b, c10::optional<torch::Tensor> bias, bool relu, bool out_fp32) {
+  using namespace gemm;
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.scalar_type() == torch::kBFloat16 && b.scalar_type() == torch::kBFloat16,
+              "gemm_bf16_tn: bf16 CUDA tensors expected");
+  TORCH_CHECK(a.is_contiguous() && b.is_contiguous(), "gemm_bf16_tn: contiguous (K-major) operands expected");
+  const bool batched = a.dim() == 3;
+  TORCH_CHECK((a.dim() == 2 || a.dim() == 3) && (b.dim() == 2 || b.dim() == a.dim()), "bad ranks");
+  const int64_t G = batched ? a.size(0) : 1;
+  const int64_t M = a.size(-2), K = a.size(-1), N = b.size(-2);
+  TORCH_CHECK(b.size(-1) == K, "K mismatch");
+  TORCH_CHECK(K % 8 == 0, "K must be a multiple of 8 (16-byte TMA row pitch)");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(a.data_ptr()) % 16 == 0 && reinterpret_cast<uintptr_t>(b.data_ptr()) % 16 == 0);
+  const c10::cuda::CUDAGuard guard(a.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  auto opts = a.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16);
+  torch::Tensor c = batched ? torch::empty({G, M, N}, opts) : torch::empty({M, N}, opts);
+  if (M == 0 || N == 0) return c;
+  const int block_n = N <= 64 ? 64 : 128;
+  const int64_t b_bstride = (b.dim() == 3) ? N * K : 0;
+  CUtensorMap ma = make_map(a.data_ptr(), G, M, K, M * K, BLOCK_M);
+  CUtensorMap mb = make_map(b.data_ptr(), b.dim() == 3 ? G : 1, N, K, b_bstride == 0 ? N * K : b_bstride, block_n);
+  EpilogueParams ep;
+  ep.C = c.data_ptr();
+  ep.bias = nullptr;
+  torch::Tensor bias_f;
+  if (bias.has_value()) {
+    bias_f = bias->to(torch::kFloat32).contiguous();
+    TORCH_CHECK(bias_f.numel() == N, "bias size mismatch");
+    ep.bias = bias_f.data_ptr<float>();
+  }
+  ep.M = static_cast<int>(M); ep.N = static_cast<int>(N); ep.K = static_cast<int>(K);
+  ep.c_batch_stride = M * N;
+  ep.relu = relu ? 1 : 0;
+  ep.out_fp32 = out_fp32 ? 1 : 0;
+  // a 2-D (shared) B is addressed with batch coordinate 0 for every g: give it a 1-deep batch dim and clamp in-kernel
+  if (b.dim() == 2 && G > 1) {
+    // replicate the map's batch extent so coordinate g is in range while the stride is 0 bytes is illegal for TMA;
+    // instead run the batches as one tall GEMM (A is [G*M, K] contiguous) — identical result, one launch.
+    CUtensorMap ma2 = make_map(a.data_ptr(), 1, G * M, K, G * M * K, BLOCK_M);
+    ep.M = static_cast<int>(G * M);
+    ep.c_batch_stride = 0;
+    if (block_n == 64) launch<64>(ma2, mb, ep, 1, stream); else launch<128>(ma2, mb, ep, 1, stream);
+    return c;
+  }
+  if (block_n == 64) launch<64>(ma, mb, ep, static_cast<int>(G), stream); else launch<128>(ma, mb, ep, static_cast<int>(G), stream);
+  return c;
+}
+
+}  // namespace flute

@@ -1,0 +1,227 @@
+"""CUDA kernels vs their PyTorch fp32 references (run on the B200 box: ``pytest -m gpu``)."""
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ext():
+    from msrflute_b200.ops import _ext
+    return _ext.load(required=True)
+
+
+def _cpu_ref(fn, *tensors, **kw):
+    """Run an arena op on CPU copies (the PyTorch reference path) and return the copies."""
+    cp = [t.detach().cpu().clone() if torch.is_tensor(t) else t for t in tensors]
+    fn(*cp, **kw)
+    return cp
+
+
+@pytest.mark.parametrize("S,P", [(1, 128), (3, 4096 + 32), (10, 1 << 20), (2, 11_700_000 // 32 * 32)])
+@pytest.mark.parametrize("momentum", [0.0, 0.9])
+def test_fused_client_step(S, P, momentum):
+    from msrflute_b200.ops import arena_ops
+    _ext()
+    torch.manual_seed(0)
+    w = torch.randn(S, P, device="cuda")
+    g = torch.randn(S, P, device="cuda") * 2
+    mom = torch.randn(S, P, device="cuda") if momentum else None
+    first = torch.zeros(S, dtype=torch.int32, device="cuda") if momentum else None
+    if first is not None:
+        first[0] = 1
+    hyper = arena_ops.make_hyper(S, "cuda", lr=0.1, max_norm=5.0, weight_decay=0.01, momentum=momentum)
+    hyper[-1, 1] = 0.0                                            # last row: clipping disabled
+    stats = torch.rand(S, 4, device="cuda")
+    ref = _cpu_ref(arena_ops.fused_client_step, w, g, hyper, stats, mom, n_logical=P - 7, nesterov=bool(momentum),
+                   first_step=first)
+    arena_ops.fused_client_step(w, g, hyper, stats, mom, n_logical=P - 7, nesterov=bool(momentum), first_step=first)
+    torch.cuda.synchronize()
+    assert torch.allclose(w.cpu(), ref[0], atol=1e-5, rtol=1e-5)
+    assert torch.all(g == 0)
+    assert torch.allclose(stats.cpu(), ref[3], rtol=2e-4, atol=1e-2)
+    if mom is not None:
+        assert torch.allclose(mom.cpu(), ref[4], atol=1e-5, rtol=1e-5)
+
+
+def test_clip_and_stats_and_pseudo_grad_and_accumulate():
+    from msrflute_b200.ops import arena_ops
+    _ext()
+    torch.manual_seed(1)
+    S, P = 5, 65536 + 64
+    g = torch.randn(S, P, device="cuda") * 4
+    hyper = arena_ops.make_hyper(S, "cuda", lr=0.0, max_norm=3.0)
+    stats = torch.zeros(S, 4, device="cuda")
+    ref = _cpu_ref(arena_ops.clip_and_stats, g, hyper, stats, n_logical=P)
+    arena_ops.clip_and_stats(g, hyper, stats, n_logical=P)
+    assert torch.allclose(g.cpu(), ref[0], atol=1e-6, rtol=1e-5)
+    assert torch.allclose(stats.cpu(), ref[2], rtol=2e-4, atol=1e-2)
+
+    wg, wl = torch.randn(P, device="cuda"), torch.randn(S, P, device="cuda")
+    out, st = torch.empty(P, device="cuda"), torch.zeros(4, device="cuda")
+    arena_ops.pseudo_grad(wg, wl[1], out, torch.tensor(2.5, device="cuda"), st)
+    assert torch.allclose(out, 2.5 * (wg - wl[1]), atol=1e-6)
+    assert math.isclose(st[1].item(), ((wg - wl[1]) ** 2).sum().item(), rel_tol=1e-4)
+
+    acc = torch.randn(P, device="cuda")
+    wts = torch.tensor([1.0, 100.0, 0.0, 3.5, 20.0], device="cuda")
+    act = torch.tensor([1, 1, 1, 0, 1], dtype=torch.int32, device="cuda")
+    expect = acc + ((wg[None] - wl) * (wts * act)[:, None]).sum(0)
+    arena_ops.accumulate_pseudo_grad(acc, wg, wl, wts, act)
+    assert torch.allclose(acc, expect, atol=1e-3, rtol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["sgd", "adam", "adamW", "adamax", "lamb", "LarsSGD"])
+@pytest.mark.parametrize("clip", [None, 0.5])
+def test_server_update_kernel(kind, clip):
+    from msrflute_b200.ops import arena_ops
+    from msrflute_b200.parallel.arena import ArenaLayout
+    _ext()
+    torch.manual_seed(2)
+    lay = ArenaLayout([torch.Size([64, 33]), torch.Size([64]), torch.Size([10, 64]), torch.Size([10])])
+    P = lay.padded_numel
+    mask = torch.zeros(P)
+    for v in lay.views(mask):
+        v.fill_(1.0)
+    w0 = torch.randn(P) * mask
+    kw = dict(lr=0.01, weight_decay=0.01 if kind != "sgd" else 0.0, momentum=0.9 if kind in ("sgd", "LarsSGD") else 0.0,
+              eps=1e-6 if kind in ("adamW", "lamb") else 1e-8)
+    st_gpu = arena_ops.ServerOptState(kind, P, "cuda", **kw)
+    st_cpu = arena_ops.ServerOptState(kind, P, "cpu", **kw)
+    w_gpu, w_cpu = w0.cuda(), w0.clone()
+    peer = torch.zeros(P, device="cuda")
+    for it in range(3):
+        accs = [torch.randn(P) * mask for _ in range(3)]
+        wsum = torch.tensor(7.0)
+        stats = torch.zeros(2, device="cuda")
+        arena_ops.server_update(w_gpu, [a.cuda() for a in accs], wsum.cuda(), st_gpu, max_grad_norm=clip,
+                                segments=lay.segments("cuda"), bcast=[w_gpu, peer], stats_out=stats if clip else None)
+        arena_ops.server_update(w_cpu, [a.clone() for a in accs], wsum, st_cpu, max_grad_norm=clip,
+                                segments=lay.segments())
+        assert torch.allclose(w_gpu.cpu(), w_cpu, atol=3e-5, rtol=1e-4), (kind, it, (w_gpu.cpu() - w_cpu).abs().max())
+        assert torch.equal(peer, w_gpu)                            # fused broadcast into the peer buffer
+        if clip:
+            g = sum(accs) / 7.0
+            assert math.isclose(stats[0].item(), g.norm().item(), rel_tol=1e-4)
+
+
+def test_server_update_dp_noise_statistics_and_invariance():
+    from msrflute_b200.ops import arena_ops
+    _ext()
+    P = 1 << 20
+    st = arena_ops.ServerOptState("sgd", P, "cuda", lr=1.0)
+    outs = []
+    for split in (1, 3):                                         # same total, different number of "ranks"
+        w = torch.zeros(P, device="cuda")
+        accs = [torch.zeros(P, device="cuda") for _ in range(split)]
+        arena_ops.server_update(w, accs, torch.tensor(1.0, device="cuda"), st, noise_scale=0.25, seed=1234)
+        outs.append(w.clone())
+    assert torch.equal(outs[0], outs[1])                         # Philox keyed by element index only
+    z = -outs[0] / 0.25
+    assert abs(z.mean().item()) < 5e-3 and abs(z.std().item() - 1.0) < 5e-3
+    w2 = torch.zeros(P, device="cuda")
+    arena_ops.server_update(w2, [torch.zeros(P, device="cuda")], torch.tensor(1.0, device="cuda"), st, noise_scale=0.25,
+                            seed=99)
+    assert not torch.equal(w2, outs[0])
+
+
+@pytest.mark.parametrize("shape,cpg", [((20, 64, 16, 16), 2), ((20, 128, 4, 4), 2), ((20, 512, 1, 1), 2), ((4, 32, 7, 5), 8)])
+@pytest.mark.parametrize("per_group", [True, False])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("fuse", [(False, False), (True, True)])
+def test_group_norm_fwd_bwd(shape, cpg, per_group, dtype, fuse):
+    from msrflute_b200.ops import norm_ops
+    _ext()
+    use_res, relu = fuse
+    torch.manual_seed(3)
+    N, C = shape[:2]
+    G = C // cpg
+    x = (torch.randn(shape, device="cuda") * 2 + 0.5).to(dtype).requires_grad_(True)
+    res = torch.randn(shape, device="cuda").to(dtype).requires_grad_(True) if use_res else None
+    A = G if per_group else C
+    wt = (torch.rand(A, device="cuda") + 0.5).requires_grad_(True)
+    b = torch.randn(A, device="cuda").requires_grad_(True)
+    y = norm_ops.group_norm(x, G, wt, b, 1e-5, residual=res, relu=relu, per_group_affine=per_group)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    got = [y.detach().float(), x.grad.float(), wt.grad.clone(), b.grad.clone()] + ([res.grad.float()] if use_res else [])
+    x2 = x.detach().float().requires_grad_(True)
+    r2 = res.detach().float().requires_grad_(True) if use_res else None
+    w2, b2 = wt.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    y2 = norm_ops._group_norm_ref(x2, G, w2, b2, 1e-5, r2, relu, per_group)
+    y2.backward(dy.float())
+    want = [y2.detach(), x2.grad, w2.grad, b2.grad] + ([r2.grad] if use_res else [])
+    tol = dict(atol=2e-4, rtol=2e-4) if dtype == torch.float32 else dict(atol=6e-2, rtol=6e-2)
+    for a, e in zip(got, want):
+        assert torch.allclose(a, e, **tol), (a - e).abs().max()
+
+
+def test_engine_round_matches_generic_path():
+    """One FedAvg round through the device engine (graphs, slots, fused accumulate) == the generic per-client path."""
+    import bench
+    from msrflute_b200.core import client as client_mod
+    torch.manual_seed(0)
+    job = bench.build_flagship(n_clients_per_round=3, users=12, norm="gn")
+    srv, worker = job.server, job.worker
+    assert worker.engine is not None
+    srv.begin_training()
+    from msrflute_b200.parallel.arena import module_arena
+    w0 = module_arena(srv.worker_trainer.model)[0].flat.clone()
+    ids = [0, 5, 7]
+    worker.set_weights(w0)
+    worker.accumulator().zero_()
+    outs_e = worker.engine.train_clients(ids, 0.1, 0, worker.weight_buffer(), worker.accumulator())
+    acc_e = worker.accumulator().clone()
+    worker.accumulator().zero_()
+    eng, worker.engine = worker.engine, None
+    outs_g = worker.train_clients(ids, (0.1, None, 0), fused=True)
+    acc_g = worker.accumulator().clone()
+    worker.engine = eng
+    # same data, different shuffles => compare scale, sample counts and weights rather than bits
+    assert [o["ns"] for o in outs_e] == [o["ns"] for o in outs_g] == [100, 100, 100]
+    assert [o["pl"]["weight"] for o in outs_e] == [100.0] * 3
+    ne, ng = acc_e.norm().item(), acc_g.norm().item()
+    assert 0.5 < ne / ng < 2.0, (ne, ng)
+    cos = torch.dot(acc_e, acc_g) / (acc_e.norm() * acc_g.norm())
+    assert cos > 0.3, cos
+    for o in outs_e:
+        assert o["tl"] > 0 and math.isfinite(o["tl"]) and o["rg"] > 0
+    srv.end_training()
+
+
+def test_flagship_rounds_reduce_loss():
+    import bench
+    job = bench.build_flagship(n_clients_per_round=4, users=8, norm="gn")
+    losses = [job.run_round() for _ in range(6)]
+    job.close()
+    assert all(math.isfinite(l) for l in losses)
+    assert min(losses[3:]) < losses[0], losses
+
+
+@pytest.mark.parametrize("G,M,N,K", [(1, 128, 64, 64), (1, 20, 1000, 512), (1, 1280, 64, 576), (1, 320, 90, 256),
+                                     (3, 200, 130, 200), (1, 4096, 4096, 1024), (10, 80, 256, 2304)])
+@pytest.mark.parametrize("epi", [(False, False, True), (True, True, False)])
+def test_gemm_tcgen05_matches_fp32_reference(G, M, N, K, epi):
+    ext = _ext()
+    if not hasattr(ext, "gemm_bf16_tn"):
+        pytest.skip("GEMM not built")
+    use_bias, relu, out_fp32 = epi
+    torch.manual_seed(4)
+    a = torch.randn(G, M, K, device="cuda").to(torch.bfloat16)
+    b = torch.randn(G, N, K, device="cuda").to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda") if use_bias else None
+    if G == 1:
+        c = ext.gemm_bf16_tn(a[0].contiguous(), b[0].contiguous(), bias, relu, out_fp32)[None]
+    else:
+        c = ext.gemm_bf16_tn(a, b, bias, relu, out_fp32)
+    ref = torch.einsum("gmk,gnk->gmn", a.float(), b.float())
+    if use_bias:
+        ref = ref + bias
+    if relu:
+        ref = ref.relu()
+    tol = 1e-2 * math.sqrt(K) if not out_fp32 else 2e-3 * math.sqrt(K)
+    err = (c.float() - ref).abs().max().item()
+    assert err < tol, (err, tol)
+    assert c.dtype == (torch.float32 if out_fp32 else torch.bfloat16)
