@@ -276,8 +276,10 @@ class OptimizationServer(federated.Server):
 
         fused = self._use_fused()
         fused_weights = []
+        in_sync = fused and getattr(self, "_weights_in_sync", False)
+        self._weights_in_sync = False
         for client_output in self.process_clients(sampled_idx_clients, server_data, self.single_worker,
-                                                  costs=costs, fused=fused, extra=extra):
+                                                  costs=costs, fused=fused, extra=extra, sync_weights=not in_sync):
             client_stats = client_output["cs"]
             client_payload = client_output["pl"]
             if apply_privacy_metrics and "ps" in client_output:
@@ -437,7 +439,9 @@ class OptimizationServer(federated.Server):
                                               stats_out=stats_out)
         if not ok:
             return False
-        if bcast is not None:
+        if hasattr(comm, "round_done"):
+            comm.round_done(worker.accumulator())
+        if bcast is not None and self.server_trainer is None and not self.fall_back_to_best_model:
             self._weights_in_sync = True
         self.strategy.client_weights, self.strategy.client_parameters_stack = [], []
         if stats_out is not None:
@@ -455,7 +459,14 @@ class OptimizationServer(federated.Server):
         worker = self.single_worker or federated._Runtime.worker
         acc = worker.accumulator()
         ar = module_arena(self.worker_trainer.model)
-        ar[1].flat.copy_(acc)
+        comm = federated.get_comm()
+        if hasattr(comm, "peer_accumulators"):            # symmetric memory: peers were not reduced yet
+            ar[1].flat.zero_()
+            for a in comm.peer_accumulators(acc):
+                ar[1].flat.add_(a)
+            comm.round_done(acc)
+        else:
+            ar[1].flat.copy_(acc)
         acc.zero_()
         self.strategy.client_weights = list(weights)
         self.strategy.client_parameters_stack = []

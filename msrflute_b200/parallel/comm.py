@@ -168,7 +168,9 @@ def make_communicator(kind: str = "auto", device=None) -> Communicator:
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return LocalComm(device)
     backend = dist.get_backend()
-    if kind in ("auto", "symm") and backend == "nccl" and torch.cuda.is_available():
+    import os
+    want_symm = kind == "symm" or (kind == "auto" and os.environ.get("FLUTE_COMM", "") == "symm")
+    if want_symm and backend == "nccl" and torch.cuda.is_available():
         try:
             from .symm import SymmComm
             return SymmComm(device)

@@ -16,6 +16,7 @@ def _ext():
 def _cpu_ref(fn, *tensors, **kw):
     """Run an arena op on CPU copies (the PyTorch reference path) and return the copies."""
     cp = [t.detach().cpu().clone() if torch.is_tensor(t) else t for t in tensors]
+    kw = {k: (v.detach().cpu().clone() if torch.is_tensor(v) else v) for k, v in kw.items()}
     fn(*cp, **kw)
     return cp
 
