@@ -56,7 +56,8 @@ def make_config(args_task="cv_resnet_fedcifar100", n_clients_per_round=10, round
     sc["num_clients_per_iteration"] = n_clients_per_round
     sc["val_freq"], sc["rec_freq"] = 10 ** 9, 10 ** 9      # rounds only (the reference arm does the same)
     sc["initial_val"], sc["initial_rec"] = False, False
-    sc.setdefault("b200", {}).update({"comm": comm, "device_resident_data": resident})
+    sc.setdefault("b200", {}).update({"comm": comm, "device_resident_data": resident,
+                                      "wave_batched": os.environ.get("FLUTE_WAVE", "1") != "0"})
     raw["model_config"]["group_norm"] = 2 if norm == "gn" else 0
     raw["model_config"]["compute_dtype"] = compute_dtype
     return FLUTEConfig.from_dict(raw)
@@ -139,9 +140,8 @@ def main():
     e2e = None
     eng = getattr(job.worker, "engine", None)
     if not args.no_e2e and eng is not None and comm.size == 1:
-        eng.resident = False
-        eng._store.clear()
-        server.run_rounds(2)                                # pin host copies / settle
+        eng.set_resident(False)                             # keep the pack in pinned host memory, stream per round
+        server.run_rounds(2)                                # settle
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         server.run_rounds(args.steps)

@@ -1,0 +1,6 @@
+from msrflute_b200.data.federated import ArrayDataLoader
+from experiments.classif_cnn.dataloaders.dataset import Dataset
+
+
+class DataLoader(ArrayDataLoader):
+    dataset_class = Dataset

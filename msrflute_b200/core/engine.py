@@ -3,15 +3,19 @@
 The reference trains one simulated client at a time per GPU, rebuilding python objects per client and copying every
 gradient to the host every mini-batch.  A B200 is idle >95 % of the time under that regime: a ResNet-18 step on a
 20×3×32×32 batch is ~2 GFLOP.  This engine keeps S *client slots* alive on the GPU and runs a whole wave of S clients
-concurrently:
+at once:
 
 * **slots** — S model replicas whose parameters / gradients are rows of two ``[S, P]`` arenas; receiving the global
   model is one broadcast copy into ``W[S, P]``.
-* **HBM-resident shards** — every user's samples live on the device (``dataset.device_tensors``); a mini-batch is an
-  on-device gather by a ``randperm`` slice.  (``device_resident_data: false`` streams the sampled users from pinned
-  host memory once per round instead.)
-* **CUDA graphs** — per slot, ``transform → forward → backward → grads-to-arena → fused clip/stats/SGD`` is captured
-  once per batch shape and replayed; slots replay on their own streams so S graphs overlap on the 148 SMs.
+* **HBM-resident shards** — the whole federated training set is packed into one device tensor
+  (``dataset.device_tensors``); a mini-batch for ALL slots is one on-device gather.  ``device_resident_data: false``
+  keeps the pack in pinned host memory and copies only the sampled users' shards host→device each round.
+* **wave-batched step** — ``torch.func.vmap(grad_and_value(loss))`` over the slot dimension turns the S per-client
+  forward/backward passes into ONE pass of batched kernels (grouped convolutions, batched GEMMs, and this repo's
+  GroupNorm kernels through their ``vmap`` rule), followed by ONE fused clip/statistics/SGD kernel over ``[S, P]``.
+  The whole thing is captured in a CUDA graph: a 10-client × 5-step round of ResNet-18 is 5 graph replays.
+* **per-slot path** — when slots cannot move in lock-step (ragged last batches, models with buffers, ops without a
+  vmap rule) each slot replays its own captured step on its own stream.
 * **no host syncs** — losses, gradient statistics and aggregation weights stay in device tensors; the host reads one
   small ``[clients, 8]`` table per round.
 * **fused gather** — at the end of a wave ONE kernel does ``acc += Σ_s weight_s·(w_global − w_s)`` over all slots
@@ -19,7 +23,7 @@ concurrently:
 
 It produces the same ``client_output`` records as ``Client.process_round`` (fused payloads) and falls back to that
 generic path for anything it does not cover (non-SGD client optimizers, FedProx/FedLabels, local DP, quantization,
-privacy metrics, personalization, ragged/text batches).
+privacy metrics, personalization, text batches).
 """
 from __future__ import annotations
 
@@ -27,7 +31,7 @@ import copy
 import logging
 import math
 import time
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import numpy as np
 import torch
@@ -40,14 +44,23 @@ from . import client as client_mod
 REC_LOSS, REC_SUM, REC_SUMSQ, REC_COUNT, REC_NS, REC_WEIGHT, REC_STEPS, REC_PAD = range(8)
 
 
+class _LossModule(torch.nn.Module):
+    def __init__(self, m):
+        super().__init__()
+        self.m = m
+
+    def forward(self, batch):
+        return self.m.loss(batch)
+
+
 class _Slot:
-    def __init__(self, idx, model, w_row, g_row, device):
+    def __init__(self, idx, model, device):
         self.idx = idx
         self.model = model
-        self.w_row, self.g_row = w_row, g_row
         self.stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
         self.graphs: Dict[tuple, object] = {}
         self.static: Dict[tuple, dict] = {}
+        self.pool = None
         self.params = [p for p in model.parameters()]
         self.grad_views = module_arena(model)[1].views()
         self.kernels_per_replay: Dict[tuple, int] = {}
@@ -68,15 +81,19 @@ class DeviceClientEngine:
         self.device = next(worker.model.parameters()).device
         self.use_graphs = bool(b200.get("cuda_graphs", True)) and self.device.type == "cuda"
         self.resident = bool(b200.get("device_resident_data", True))
+        self.want_wave = bool(b200.get("wave_batched", True))
         ncpi = config["server_config"]["num_clients_per_iteration"]
         ncpi = max(int(x) for x in ncpi.split(",")) if isinstance(ncpi, str) else int(ncpi)
-        self.S = max(1, min(int(b200.get("max_concurrent_clients", 16)), ncpi))
+        import os as _os
+        world = int(_os.environ.get("WORLD_SIZE", 1))
+        workers = world if (world == 1 or b200.get("server_is_worker", True)) else world - 1
+        share = math.ceil(ncpi / max(workers, 1)) + (1 if workers > 1 else 0)   # LPT may give one rank an extra client
+        self.S = max(1, min(int(b200.get("max_concurrent_clients", 16)), share))
         self.dataset = client_mod.train_dataset
-        self._store: Dict[str, dict] = {}
-        self._pinned: Dict[str, dict] = {}
         self._built = False
         self.h2d_bytes_last_round = 0
-        self.pool = None
+        self.d2h_bytes_last_round = 0
+        self.wave_ok = None          # None = untried, True/False after the first attempt
 
     # ------------------------------------------------------------------ capability
     def supports(self, cfg) -> bool:
@@ -118,7 +135,7 @@ class DeviceClientEngine:
                     delattr(m, attr)
             adopt_module(m, with_grad=True, param_buffer=self.W[s], grad_buffer=self.G[s])
             m.train()
-            self.slots.append(_Slot(s, m, self.W[s], self.G[s], dev))
+            self.slots.append(_Slot(s, m, dev))
         self.hyper = arena_ops.make_hyper(self.S, dev)
         self.stats = torch.zeros(self.S, 4, device=dev)
         self.loss_sum = torch.zeros(self.S, device=dev)
@@ -131,33 +148,78 @@ class DeviceClientEngine:
         self.nesterov = bool(opt.get("nesterov", False))
         self.dampening = float(opt.get("dampening", 0.0) or 0.0)
         self.weight_decay = float(opt.get("weight_decay", 0.0) or 0.0)
-        if self.resident:
-            t0 = time.time()
-            for u in self.dataset.user_list:
-                self._user_tensors(u)
-            print_rank("device engine: {} users resident in HBM ({:.1f} MB) in {:.1f}s".format(
-                len(self._store), sum(v["x"].numel() * v["x"].element_size() for v in self._store.values()) / 2 ** 20,
-                time.time() - t0), logging.INFO)
+        self._pack_dataset()
+        # stacked (strided) per-parameter views over the slot arenas for the vmapped step
+        names = [n for n, _ in base.named_parameters()]
+        lay = self.layout
+        self.param_stack = {"m." + n: self.W[:, o:o + k].view((self.S,) + tuple(sh))
+                            for n, o, k, sh in zip(names, lay.offsets, lay.sizes, lay.shapes)}
+        self.grad_stack = [self.G[:, o:o + k].view((self.S,) + tuple(sh))
+                           for o, k, sh in zip(lay.offsets, lay.sizes, lay.shapes)]
+        self.param_names = ["m." + n for n in names]
+        self.has_buffers = any(True for _ in base.buffers())
+        self.loss_module = _LossModule(self.slots[0].model)
+        self.slot_model = None
+        if self.device.type == "cuda" and self.want_wave:
+            from ..models.slot_resnet import SlotBatchedResNet
+            ext = _ext.load()
+            if ext is not None and hasattr(ext, "slot_conv_fprop") and SlotBatchedResNet.supports(base):
+                self.slot_model = SlotBatchedResNet(self.slots[0].model, self.layout, self.W, self.G)
+                print_rank("device engine: slot-batched hand-written conv/GroupNorm path enabled", logging.INFO)
+        self.wave_graphs: Dict[tuple, object] = {}
+        self.wave_static: Dict[tuple, dict] = {}
+        self.wave_kernels: Dict[tuple, int] = {}
+        self.wave_pool = None
         self._built = True
 
-    def _user_tensors(self, user):
-        t = self._store.get(user)
-        if t is not None:
-            return t
+    def _pack_dataset(self):
+        """One contiguous (pinned) pack of every user's raw samples + per-user offsets; uploaded once if resident."""
+        t0 = time.time()
+        ds = self.dataset
+        xs, ys, off = [], [], [0]
+        for u in ds.user_list:
+            t = ds.device_tensors(u)
+            xs.append(t["x"])
+            ys.append(t["y"])
+            off.append(off[-1] + int(t["x"].shape[0]))
+        self.offsets = off
+        X, Y = torch.cat(xs), torch.cat(ys)
+        cuda = self.device.type == "cuda"
         if self.resident:
-            raw = self.dataset.device_tensors(user)
-            t = {k: v.to(self.device) for k, v in raw.items()}
-            self._store[user] = t
-            return t
-        pin = self._pinned.get(user)
-        if pin is None:
-            raw = self.dataset.device_tensors(user)
-            pin = {k: (v.pin_memory() if self.device.type == "cuda" else v) for k, v in raw.items()}
-            self._pinned[user] = pin
-        self.h2d_bytes_last_round += sum(v.numel() * v.element_size() for v in pin.values())
-        return {k: v.to(self.device, non_blocking=True) for k, v in pin.items()}
+            self.X, self.Y = X.to(self.device), Y.to(self.device)
+            self.Xh = self.Yh = None
+        else:
+            self.Xh, self.Yh = (X.pin_memory(), Y.pin_memory()) if cuda else (X, Y)
+            max_n = max(b - a for a, b in zip(off[:-1], off[1:]))
+            self.X = torch.empty((self.S * max_n,) + tuple(X.shape[1:]), dtype=X.dtype, device=self.device)
+            self.Y = torch.empty((self.S * max_n,) + tuple(Y.shape[1:]), dtype=Y.dtype, device=self.device)
+            self.stage_rows = max_n
+        print_rank("device engine: packed {} users / {} samples ({:.1f} MB, {}) in {:.1f}s".format(
+            len(ds.user_list), off[-1], X.numel() * X.element_size() / 2 ** 20,
+            "HBM-resident" if self.resident else "pinned host, streamed per round", time.time() - t0), logging.INFO)
 
-    # ------------------------------------------------------------------ one mini-batch
+    def set_resident(self, resident: bool):
+        """Switch between HBM-resident and streamed inputs (bench.py's end-to-end pass)."""
+        if self._built and resident != self.resident:
+            self.resident = resident
+            self._pack_dataset()
+        else:
+            self.resident = resident
+
+    def _slot_rows(self, s, cid):
+        """(base_row, n) of client ``cid``'s samples for slot ``s`` — streaming copies the shard H2D first."""
+        a, b = self.offsets[cid], self.offsets[cid + 1]
+        n = b - a
+        if self.resident:
+            return a, n
+        base = s * self.stage_rows
+        self.X[base:base + n].copy_(self.Xh[a:b], non_blocking=True)
+        self.Y[base:base + n].copy_(self.Yh[a:b], non_blocking=True)
+        self.h2d_bytes_last_round += (b - a) * (self.Xh[0].numel() * self.Xh.element_size()
+                                                + self.Yh[0].numel() * self.Yh.element_size())
+        return base, n
+
+    # ------------------------------------------------------------------ per-slot mini-batch
     def _step_body(self, slot: _Slot, xraw, y):
         batch = {"x": self.dataset.transform_batch(xraw), "y": y}
         loss = slot.model.loss(batch)
@@ -174,36 +236,100 @@ class DeviceClientEngine:
             self.first[s:s + 1].zero_()
         self.loss_sum[s:s + 1] += loss.detach().float().reshape(1)
 
-    def _run_step(self, slot: _Slot, x_user, y_user, idx):
-        key = (tuple(x_user.shape[1:]), x_user.dtype, int(idx.numel()))
+    def _run_step(self, slot: _Slot, idx):
+        key = int(idx.numel())
         if not self.use_graphs:
-            self._step_body(slot, x_user.index_select(0, idx), y_user.index_select(0, idx))
+            self._step_body(slot, self.X.index_select(0, idx), self.Y.index_select(0, idx))
             return
         st = slot.static.get(key)
         if st is None:
-            st = {"x": torch.empty((idx.numel(),) + tuple(x_user.shape[1:]), dtype=x_user.dtype, device=self.device),
-                  "y": torch.empty((idx.numel(),) + tuple(y_user.shape[1:]), dtype=y_user.dtype, device=self.device),
-                  "uses": 0}
+            st = {"x": torch.empty((key,) + tuple(self.X.shape[1:]), dtype=self.X.dtype, device=self.device),
+                  "y": torch.empty((key,) + tuple(self.Y.shape[1:]), dtype=self.Y.dtype, device=self.device), "uses": 0}
             slot.static[key] = st
-        torch.index_select(x_user, 0, idx, out=st["x"])
-        torch.index_select(y_user, 0, idx, out=st["y"])
+        torch.index_select(self.X, 0, idx, out=st["x"])
+        torch.index_select(self.Y, 0, idx, out=st["y"])
         g = slot.graphs.get(key)
         if g is None:
             st["uses"] += 1
-            if st["uses"] <= 2:          # warm-up eagerly (also initialises cuDNN/cuBLAS handles on this stream)
+            if st["uses"] <= 2:          # warm up eagerly (cuDNN/cuBLAS handles + autotune on this stream)
                 self._step_body(slot, st["x"], st["y"])
                 return
             g = torch.cuda.CUDAGraph()
             n0 = _ext.LAUNCH_COUNTER["n"]
-            with torch.cuda.graph(g, stream=slot.stream, pool=self.pool):
-                self._step_body(slot, st["x"], st["y"])
-            if self.pool is None:
-                self.pool = g.pool()
+            with torch.cuda.graph(g, stream=slot.stream, pool=slot.pool):   # one private pool PER SLOT:
+                self._step_body(slot, st["x"], st["y"])                     # slots replay concurrently
+            if slot.pool is None:
+                slot.pool = g.pool()
             slot.kernels_per_replay[key] = _ext.LAUNCH_COUNTER["n"] - n0
             slot.graphs[key] = g
-            # capture does not execute: fall through and replay so this step really happens
         g.replay()
         _ext.count_launch(slot.kernels_per_replay.get(key, 0))
+
+    # ------------------------------------------------------------------ wave-batched mini-batch (all slots at once)
+    def _wave_body(self, xw, yw):
+        if self.slot_model is not None:
+            S, B = xw.shape[0], xw.shape[1]
+            xb = self.dataset.transform_batch(xw.reshape((S * B,) + tuple(xw.shape[2:])))
+            losses = self.slot_model.losses(xb.reshape((S, B) + tuple(xb.shape[1:])), yw)
+            losses.sum().backward()                    # weight grads are accumulated into self.G by the kernels
+            arena_ops.fused_client_step(self.W, self.G, self.hyper, self.stats, self.M, n_logical=self.layout.numel,
+                                        nesterov=self.nesterov, dampening=self.dampening, zero_grad=True,
+                                        first_step=self.first)
+            if self.first is not None:
+                self.first.zero_()
+            self.loss_sum += losses.detach().float()
+            return
+        from torch.func import functional_call, grad_and_value, vmap
+
+        def loss_fn(p, xb, yb):
+            return functional_call(self.loss_module, p, ({"x": self.dataset.transform_batch(xb), "y": yb},))
+
+        grads, losses = vmap(grad_and_value(loss_fn), in_dims=(0, 0, 0), randomness="different")(self.param_stack, xw, yw)
+        torch._foreach_copy_(self.grad_stack, [grads[n] for n in self.param_names])
+        arena_ops.fused_client_step(self.W, self.G, self.hyper, self.stats, self.M, n_logical=self.layout.numel,
+                                    nesterov=self.nesterov, dampening=self.dampening, zero_grad=True,
+                                    first_step=self.first)
+        if self.first is not None:
+            self.first.zero_()
+        self.loss_sum += losses.detach().float()
+
+    def _run_wave_step(self, idx2d):
+        """``idx2d``: [S, B] global sample rows.  Returns False if this model cannot be vmapped (caller falls back)."""
+        B = int(idx2d.shape[1])
+        st = self.wave_static.get(B)
+        if st is None:
+            st = {"x": torch.empty((self.S, B) + tuple(self.X.shape[1:]), dtype=self.X.dtype, device=self.device),
+                  "y": torch.empty((self.S, B) + tuple(self.Y.shape[1:]), dtype=self.Y.dtype, device=self.device), "uses": 0}
+            self.wave_static[B] = st
+        flat = idx2d.reshape(-1)
+        torch.index_select(self.X, 0, flat, out=st["x"].view((self.S * B,) + tuple(self.X.shape[1:])))
+        torch.index_select(self.Y, 0, flat, out=st["y"].view((self.S * B,) + tuple(self.Y.shape[1:])))
+        g = self.wave_graphs.get(B)
+        if g is None:
+            st["uses"] += 1
+            if st["uses"] <= 2 or not self.use_graphs:
+                try:
+                    self._wave_body(st["x"], st["y"])
+                except Exception as e:  # no vmap rule for some op in this model → per-slot path from now on
+                    if self.wave_ok is None:
+                        print_rank("wave-batched step unavailable for this model ({}: {}); using per-slot graphs"
+                                   .format(type(e).__name__, str(e).split("\n")[0][:160]), logging.WARNING)
+                        self.wave_ok = False
+                        return False
+                    raise
+                self.wave_ok = True
+                return True
+            g = torch.cuda.CUDAGraph()
+            n0 = _ext.LAUNCH_COUNTER["n"]
+            with torch.cuda.graph(g, pool=self.wave_pool):
+                self._wave_body(st["x"], st["y"])
+            if self.wave_pool is None:
+                self.wave_pool = g.pool()
+            self.wave_kernels[B] = _ext.LAUNCH_COUNTER["n"] - n0
+            self.wave_graphs[B] = g
+        g.replay()
+        _ext.count_launch(self.wave_kernels.get(B, 0))
+        return True
 
     # ------------------------------------------------------------------ a round's share
     def train_clients(self, client_ids, lr, nround, w_global, acc):
@@ -226,7 +352,7 @@ class DeviceClientEngine:
         records = torch.zeros(len(client_ids), 8, device=dev)
         hyper_row = torch.tensor([lr, max_norm or 0.0, self.weight_decay, self.momentum], dtype=torch.float32)
         self.hyper.copy_(hyper_row.to(dev, non_blocking=True).expand(self.S, 4))
-        ds = self.dataset
+        wave_mode = self.want_wave and (self.slot_model is not None or not self.has_buffers) and self.wave_ok is not False
         for wave_start in range(0, len(client_ids), self.S):
             wave = client_ids[wave_start:wave_start + self.S]
             n_act = len(wave)
@@ -235,39 +361,57 @@ class DeviceClientEngine:
             self.loss_sum.zero_()
             if self.first is not None:
                 self.first.fill_(1)
-            plans = []
-            for s, cid in enumerate(wave):
-                user = ds.user_list[cid]
-                t = self._user_tensors(user)
-                n = int(t["x"].shape[0])
+            rows = [self._slot_rows(s, cid) for s, cid in enumerate(wave)]
+            ns = [n for _, n in rows]
+            nbs = []
+            for n in ns:
                 nb = math.ceil(n / bs)
                 if desired is not None:
                     nb = min(nb, max(1, math.ceil(desired / bs)))
-                perm = torch.randperm(n, device=dev)
-                plans.append((t, n, nb, perm))
-            if main is not None:
-                for slot in self.slots[:n_act]:
-                    slot.stream.wait_stream(main)
-            max_nb = max(p[2] for p in plans) if plans else 0
-            ns_list = [0] * n_act
-            for b in range(max_nb):                                   # step-major issue order: S graphs in flight
-                for s in range(n_act):
-                    t, n, nb, perm = plans[s]
-                    if b >= nb:
-                        continue
-                    idx = perm[b * bs:min((b + 1) * bs, n)]
-                    slot = self.slots[s]
-                    if slot.stream is not None:
-                        with torch.cuda.stream(slot.stream):
-                            self._run_step(slot, t["x"], t["y"], idx)
-                    else:
-                        self._run_step(slot, t["x"], t["y"], idx)
-                    ns_list[s] += int(idx.numel())
-            if main is not None:
-                for slot in self.slots[:n_act]:
-                    main.wait_stream(slot.stream)
+                nbs.append(nb)
+            # on-device shuffles: one [S, n] argsort when all users have the same size, else per-slot randperm
+            if len(set(ns)) == 1:
+                bases = [b for b, _ in rows] + [rows[0][0]] * (self.S - n_act)   # idle slots re-read slot 0's shard
+                perm = torch.rand(self.S, ns[0], device=dev).argsort(dim=1)
+                perm = perm + torch.tensor(bases, device=dev).view(-1, 1)
+                perms = None
+            else:
+                perm = None
+                perms = [torch.randperm(n, device=dev) + b for b, n in rows]
+            full_steps = min(min(nb, n // bs) for n, nb in zip(ns, nbs))   # steps every slot runs with a full batch
+            ns_done = [0] * n_act
+            b0 = 0
+            if wave_mode and perm is not None and full_steps > 0:
+                for b in range(full_steps):
+                    if not self._run_wave_step(perm[:, b * bs:(b + 1) * bs]):
+                        wave_mode = False
+                        break
+                    b0 = b + 1
+                    for s in range(n_act):
+                        ns_done[s] += bs
+            if b0 < max(nbs):
+                # per-slot path for whatever could not run in lock-step
+                if main is not None:
+                    for slot in self.slots[:n_act]:
+                        slot.stream.wait_stream(main)
+                for b in range(b0, max(nbs)):
+                    for s in range(n_act):
+                        if b >= nbs[s]:
+                            continue
+                        p = perm[s] if perm is not None else perms[s]
+                        idx = p[b * bs:min((b + 1) * bs, ns[s])]
+                        slot = self.slots[s]
+                        if slot.stream is not None:
+                            with torch.cuda.stream(slot.stream):
+                                self._run_step(slot, idx)
+                        else:
+                            self._run_step(slot, idx)
+                        ns_done[s] += int(idx.numel())
+                if main is not None:
+                    for slot in self.slots[:n_act]:
+                        main.wait_stream(slot.stream)
             # aggregation weights (device side, no sync)
-            ns_t = torch.tensor(ns_list + [0] * (self.S - n_act), dtype=torch.float32).to(dev, non_blocking=True)
+            ns_t = torch.tensor(ns_done + [0] * (self.S - n_act), dtype=torch.float32).to(dev, non_blocking=True)
             if softmax:
                 kind = sc.get("weight_train_loss", "train_loss")
                 mean_, mag_, var_, _ = arena_ops.finalize_stats(self.stats)

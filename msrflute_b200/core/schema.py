@@ -34,7 +34,7 @@ def _loader_common():
         "batch_size": _opt("integer", default=40),
         "tokenizer_type": _opt("string"),
         "prepend_datapath": _opt("boolean", default=False),
-        "vocab_dict": _opt("string"),
+        "vocab_dict": _opt("string", nullable=True),
         "pin_memory": _opt("boolean", default=True),
         "num_workers": _opt("integer", default=1),
         "num_frames": _opt("integer", default=0),
@@ -88,6 +88,7 @@ B200_KEYS = {
     "seed": _opt("integer", default=0),
     "async_checkpoint": _opt("boolean"),
     "device_engine": _opt("boolean", default=True),
+    "wave_batched": _opt("boolean", default=True),
 }
 
 

@@ -19,14 +19,33 @@ void server_update(torch::Tensor w, std::vector<torch::Tensor> accs, torch::Tens
 void p2p_broadcast(torch::Tensor src, std::vector<torch::Tensor> dsts);
 std::vector<torch::Tensor> group_norm_fwd(torch::Tensor x, torch::Tensor weight, torch::Tensor bias,
                                           c10::optional<torch::Tensor> residual, int64_t G, double eps, bool relu,
-                                          bool per_group_affine);
+                                          bool per_group_affine, int64_t sets);
 std::vector<torch::Tensor> group_norm_bwd(torch::Tensor dy, torch::Tensor x, torch::Tensor weight, torch::Tensor mean,
                                           torch::Tensor rstd, c10::optional<torch::Tensor> y, int64_t G, bool relu,
-                                          bool per_group_affine, bool has_residual);
-#ifdef FLUTE_WITH_GEMM
+                                          bool per_group_affine, bool has_residual, int64_t sets);
+
 torch::Tensor gemm_bf16_tn(torch::Tensor a, torch::Tensor b, c10::optional<torch::Tensor> bias, bool relu,
                            bool out_fp32);
-#endif
+
+
+at::Tensor gru_cell_fwd(at::Tensor gi, at::Tensor gh, at::Tensor h);
+std::vector<at::Tensor> gru_cell_bwd(at::Tensor dh, at::Tensor gi, at::Tensor gh, at::Tensor h);
+std::vector<at::Tensor> lstm_cell_fwd(at::Tensor gates, at::Tensor c);
+std::vector<at::Tensor> lstm_cell_bwd(at::Tensor dh, at::Tensor dc, at::Tensor gates, at::Tensor c, at::Tensor c2);
+
+std::vector<torch::Tensor> group_norm_fwd_arena(torch::Tensor x, torch::Tensor w_arena, int64_t w_off, int64_t b_off,
+                                                c10::optional<torch::Tensor> residual, int64_t G, double eps, bool relu,
+                                                bool per_group_affine, int64_t sets);
+std::vector<torch::Tensor> group_norm_bwd_arena(torch::Tensor dy, torch::Tensor x, torch::Tensor w_arena, int64_t w_off,
+                                                torch::Tensor mean, torch::Tensor rstd, c10::optional<torch::Tensor> y,
+                                                int64_t G, bool relu, bool per_group_affine, bool has_residual,
+                                                int64_t sets, torch::Tensor g_arena, int64_t gw_off, int64_t gb_off);
+at::Tensor slot_conv_fprop(at::Tensor x, at::Tensor w_arena, int64_t w_offset, int64_t Cout, int64_t KH, int64_t KW,
+                           int64_t stride, int64_t pad);
+at::Tensor slot_conv_dgrad(at::Tensor dy, at::Tensor w_arena, int64_t w_offset, int64_t Cin, int64_t Hi, int64_t Wi,
+                           int64_t KH, int64_t KW, int64_t stride, int64_t pad);
+void slot_conv_wgrad(at::Tensor x, at::Tensor dy, at::Tensor g_arena, int64_t g_offset, int64_t KH, int64_t KW,
+                     int64_t stride, int64_t pad);
 }  // namespace flute
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -39,7 +58,18 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("p2p_broadcast", &flute::p2p_broadcast);
   m.def("group_norm_fwd", &flute::group_norm_fwd);
   m.def("group_norm_bwd", &flute::group_norm_bwd);
-#ifdef FLUTE_WITH_GEMM
+
   m.def("gemm_bf16_tn", &flute::gemm_bf16_tn);
-#endif
+
+
+  m.def("group_norm_fwd_arena", &flute::group_norm_fwd_arena);
+  m.def("group_norm_bwd_arena", &flute::group_norm_bwd_arena);
+  m.def("slot_conv_fprop", &flute::slot_conv_fprop);
+  m.def("slot_conv_dgrad", &flute::slot_conv_dgrad);
+  m.def("slot_conv_wgrad", &flute::slot_conv_wgrad);
+  m.def("gru_cell_fwd", &flute::gru_cell_fwd);
+  m.def("gru_cell_bwd", &flute::gru_cell_bwd);
+  m.def("lstm_cell_fwd", &flute::lstm_cell_fwd);
+  m.def("lstm_cell_bwd", &flute::lstm_cell_bwd);
+
 }

@@ -31,10 +31,11 @@ def _sizes(rng, num_users, mean, fixed):
 
 
 def make_vector_classification(num_users=1000, mean_samples=60, dim=784, num_classes=10, seed=0, fixed=False,
-                               dtype=np.float32, prefix="u"):
-    """LR-MNIST-like: ``dim``-vectors in [0,1], ``num_classes`` labels (1000 users × ~60 in the benchmark)."""
+                               dtype=np.float32, prefix="u", proto_seed=1234):
+    """LR-MNIST-like: ``dim``-vectors in [0,1], ``num_classes`` labels (1000 users × ~60 in the benchmark).
+    Class prototypes depend on ``proto_seed`` only, so train/val/test splits (different ``seed``) share the task."""
     rng = np.random.default_rng(seed)
-    protos = rng.random((num_classes, dim)).astype(np.float32)
+    protos = np.random.default_rng(proto_seed).random((num_classes, dim)).astype(np.float32)
     st = _struct()
     for u, n in enumerate(_sizes(rng, num_users, mean_samples, fixed)):
         y = rng.integers(0, num_classes, size=n)
@@ -44,10 +45,10 @@ def make_vector_classification(num_users=1000, mean_samples=60, dim=784, num_cla
 
 
 def make_image_classification(num_users=500, mean_samples=100, shape=(32, 32, 3), num_classes=100, seed=0,
-                              fixed=True, dtype=np.uint8, prefix="u", scale=255.0):
+                              fixed=True, dtype=np.uint8, prefix="u", scale=255.0, proto_seed=1234):
     """FedCIFAR-100-like (500 users × 100 × 32×32×3 uint8, HWC) or FEMNIST-like (``shape=(28,28)``, float)."""
     rng = np.random.default_rng(seed)
-    protos = rng.random((num_classes,) + tuple(shape)).astype(np.float32)
+    protos = np.random.default_rng(proto_seed).random((num_classes,) + tuple(shape)).astype(np.float32)
     st = _struct()
     for u, n in enumerate(_sizes(rng, num_users, mean_samples, fixed)):
         y = rng.integers(0, num_classes, size=n)
@@ -57,10 +58,11 @@ def make_image_classification(num_users=500, mean_samples=100, shape=(32, 32, 3)
     return st
 
 
-def make_char_sequences(num_users=715, mean_samples=50, seq_len=80, vocab=90, seed=0, fixed=False, prefix="u"):
+def make_char_sequences(num_users=715, mean_samples=50, seq_len=80, vocab=90, seed=0, fixed=False, prefix="u",
+                        proto_seed=1234):
     """FedShakespeare-like next-char prediction: x = tokens[t], y = tokens[t+1]; 0 is the pad id."""
     rng = np.random.default_rng(seed)
-    trans = rng.dirichlet(np.full(vocab - 1, 0.05), size=vocab - 1)     # sparse Markov chain over ids 1..vocab-1
+    trans = np.random.default_rng(proto_seed).dirichlet(np.full(vocab - 1, 0.05), size=vocab - 1)  # sparse Markov chain
     cdf = np.cumsum(trans, axis=1)
     st = _struct()
     for u, n in enumerate(_sizes(rng, num_users, mean_samples, fixed)):

@@ -1,0 +1,130 @@
+"""Hermetic end-to-end runs of the FL engine on CPU (gloo), the reference's own test strategy
+(``testing/test_e2e_trainer.py``: launch e2e_trainer via torch.distributed.run, assert exit code 0) plus the
+numerical / resume assertions the reference never makes."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _write_data(tmp, users=12, per=24, seed=0):
+    from msrflute_b200.data import synthetic
+    tr = synthetic.make_vector_classification(users, per, 784, 10, seed=seed, fixed=True)
+    te = synthetic.make_vector_classification(4, per, 784, 10, seed=seed + 1, fixed=True)
+    torch.save(tr, os.path.join(tmp, "train.pt"))
+    torch.save(te, os.path.join(tmp, "test.pt"))
+
+
+def _config(tmp, rounds=3, resume=False, strategy="FedAvg", extra_server=None, extra_client=None, dp=None):
+    with open(os.path.join(ROOT, "experiments", "cv_lr_mnist", "config.yaml")) as f:
+        cfg = yaml.safe_load(f)
+    sc = cfg["server_config"]
+    sc.update({"max_iteration": rounds, "num_clients_per_iteration": 4, "val_freq": 1, "rec_freq": 2,
+               "initial_val": True, "resume_from_checkpoint": resume, "initial_lr_client": 0.5})
+    sc["data_config"]["val"].update({"val_data": "test.pt", "batch_size": 64})
+    sc["data_config"]["test"].update({"test_data": "test.pt", "batch_size": 64})
+    sc.update(extra_server or {})
+    cfg["client_config"]["data_config"]["train"].update({"list_of_train_data": "train.pt", "batch_size": 8})
+    cfg["client_config"].update(extra_client or {})
+    cfg["strategy"] = strategy
+    if dp:
+        cfg["dp_config"] = dp
+    path = os.path.join(tmp, "cfg.yaml")
+    with open(path, "w") as f:
+        yaml.safe_dump(cfg, f)
+    return path
+
+
+def _run(tmp, cfg_path, nproc=1, port=29611, timeout=900):
+    out = os.path.join(tmp, "out")
+    cmd = [sys.executable]
+    if nproc > 1:
+        cmd += ["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+                "--master-port", str(port)]
+    cmd += [os.path.join(ROOT, "e2e_trainer.py"), "-config", cfg_path, "-outputPath", out, "-dataPath", tmp,
+            "-task", "cv_lr_mnist", "-backend", "gloo", "-experiment", "exp"]
+    env = dict(os.environ, PYTHONPATH=ROOT, FLUTE_ALLOW_FALLBACK="1", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return os.path.join(out, "exp"), r.stdout + r.stderr
+
+
+def _metrics(exp):
+    out = {}
+    with open(os.path.join(exp, "log", "metrics.jsonl")) as f:
+        for line in f:
+            e = json.loads(line)
+            out.setdefault(e["k"], []).append(e["v"])
+    return out
+
+
+def test_single_process_round_loop_output_tree_and_learning(tmp_path):
+    tmp = str(tmp_path)
+    _write_data(tmp)
+    exp, log = _run(tmp, _config(tmp, rounds=6))
+    models = os.path.join(exp, "models")
+    for f in ("latest_model.tar", "best_val_loss_model.tar", "best_val_acc_model.tar", "best_test_acc_model.tar",
+              "epoch0_model.tar", "config.yaml", "status_log.json"):
+        assert os.path.exists(os.path.join(models, f)), f
+    assert os.path.exists(os.path.join(exp, "FLUTE_config.yaml")) and os.path.exists(os.path.join(exp, "log", "log.out"))
+    st = json.load(open(os.path.join(models, "status_log.json")))
+    assert st["i"] == 6 and st["best_val_loss"] < float("inf")
+    m = _metrics(exp)
+    assert len(m["Training loss"]) == 6 and len(m["secsPerRoundTotal"]) == 6
+    assert m["Val loss"][-1] < m["Val loss"][0]                          # the global model actually improves
+    ck = torch.load(os.path.join(models, "latest_model.tar"), weights_only=False)
+    assert set(ck) >= {"model_state_dict", "optimizer_state_dict", "lr_scheduler_state_dict"}
+    assert ck["model_state_dict"]["net.linear.weight"].shape == (10, 784)
+
+
+def test_resume_from_checkpoint_continues_at_saved_iteration(tmp_path):
+    tmp = str(tmp_path)
+    _write_data(tmp)
+    exp, _ = _run(tmp, _config(tmp, rounds=2))
+    w2 = torch.load(os.path.join(exp, "models", "latest_model.tar"), weights_only=False)["model_state_dict"]["net.linear.weight"].clone()
+    exp, log = _run(tmp, _config(tmp, rounds=4, resume=True))
+    assert "Resuming from status_log: cur_iter: 2" in log
+    assert "==== iteration 2" in log and "==== iteration 0" not in log
+    st = json.load(open(os.path.join(exp, "models", "status_log.json")))
+    assert st["i"] == 4
+    w4 = torch.load(os.path.join(exp, "models", "latest_model.tar"), weights_only=False)["model_state_dict"]["net.linear.weight"]
+    assert not torch.equal(w2, w4)
+
+
+@pytest.mark.parametrize("strategy,extra", [
+    ("DGA", {"server": {"aggregate_median": "softmax", "stale_prob": 0.3}, "client": {"quant_thresh": 0.5, "quant_bits": 6, "quant_anneal": 0.9}}),
+    ("DGA", {"server": {"aggregate_median": "mean", "fast_aggregation": True},
+             "dp": {"enable_local_dp": True, "enable_global_dp": True, "eps": -1.0, "max_grad": 1.0, "global_sigma": 0.01,
+                    "max_weight": 1.0, "min_weight": 0.0, "delta": 1e-6}}),
+    ("FedProx", {"client": {"mu": 0.01}}),
+])
+def test_strategies_end_to_end(tmp_path, strategy, extra):
+    tmp = str(tmp_path)
+    _write_data(tmp)
+    exp, log = _run(tmp, _config(tmp, rounds=3, strategy=strategy, extra_server=extra.get("server"),
+                                 extra_client=extra.get("client"), dp=extra.get("dp")))
+    m = _metrics(exp)
+    assert len(m["Training loss"]) == 3
+    if extra.get("dp"):
+        assert "dp_epsilon_rdp" in m and "Gradient Norm" in m
+    if "quant_thresh" in (extra.get("client") or {}):
+        assert abs(m["Quantization Thresh."][-1] - 0.5 * 0.9 ** 3) < 1e-6
+        assert "Stale Gradients Ratio" in m
+
+
+def test_two_ranks_gloo_every_rank_trains_and_server_aggregates(tmp_path):
+    """BASELINE config #1: LR-MNIST FedAvg, world_size=2 on CPU/gloo."""
+    tmp = str(tmp_path)
+    _write_data(tmp)
+    exp, log = _run(tmp, _config(tmp, rounds=3), nproc=2)
+    st = json.load(open(os.path.join(exp, "models", "status_log.json")))
+    assert st["i"] == 3
+    m = _metrics(exp)
+    assert m["Val loss"][-1] < m["Val loss"][0]
+    assert "Worker on node 1: process started" in log
