@@ -256,7 +256,9 @@ class DeviceClientEngine:
                 return
             g = torch.cuda.CUDAGraph()
             n0 = _ext.LAUNCH_COUNTER["n"]
-            with torch.cuda.graph(g, stream=slot.stream, pool=slot.pool):   # one private pool PER SLOT:
+            # thread_local: the async checkpoint writer thread may issue D2H copies while we capture
+            with torch.cuda.graph(g, stream=slot.stream, pool=slot.pool,   # one private pool PER SLOT:
+                                  capture_error_mode="thread_local"):
                 self._step_body(slot, st["x"], st["y"])                     # slots replay concurrently
             if slot.pool is None:
                 slot.pool = g.pool()
@@ -321,7 +323,7 @@ class DeviceClientEngine:
                 return True
             g = torch.cuda.CUDAGraph()
             n0 = _ext.LAUNCH_COUNTER["n"]
-            with torch.cuda.graph(g, pool=self.wave_pool):
+            with torch.cuda.graph(g, pool=self.wave_pool, capture_error_mode="thread_local"):
                 self._wave_body(st["x"], st["y"])
             if self.wave_pool is None:
                 self.wave_pool = g.pool()

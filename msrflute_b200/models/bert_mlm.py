@@ -1,0 +1,138 @@
+"""Masked-language-model fine-tuning with HuggingFace encoders (ref. ``experiments/mlm_bert/model.py``).
+
+Parity: ``model_config.BERT.{model, training}`` arguments (``model_name``, ``model_name_or_path``, ``cache_dir``,
+``use_fast_tokenizer``, ``gradient_accumulation_steps``, ``label_smoothing_factor``, ``seed``, ``batch_size`` …), loss =
+the HF MLM loss (optionally label-smoothed) divided by ``gradient_accumulation_steps`` (ref :186-245), RoBERTa inputs
+stripped of ``attention_mask`` / ``special_tokens_mask`` (ref :218-223), ``inference`` returns eval loss and masked-token
+accuracy (ref :247-366 → ``ComputeMetrics``, ``utils/trainer_utils.py:64-86``).
+
+Differences: evaluation is ONE forward per batch (the reference runs the HF ``prediction_loop`` machinery and copies all
+logits — B·S·30522 floats — to the host to compute an argmax); accuracy is computed on the device.  Without network
+access ``from_pretrained`` cannot download: a local ``model_name_or_path`` directory is used when it exists, otherwise
+the architecture named by ``model_name`` is instantiated from its config with random weights (the benchmark setting:
+"random-init weights of that architecture").  Attention runs through PyTorch SDPA (flash kernels on sm_100).
+"""
+import logging
+import os
+
+import torch as T
+
+from ..core.model import BaseModel
+from ..utils import print_rank
+
+_ARCH = {
+    # name fragment -> (hf model_type, config overrides)
+    "tiny": ("bert", dict(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128,
+                          vocab_size=1000, max_position_embeddings=128)),
+    "roberta-large": ("roberta", dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16,
+                                      intermediate_size=4096, vocab_size=50265, max_position_embeddings=514,
+                                      type_vocab_size=1)),
+    "roberta": ("roberta", dict(vocab_size=50265, max_position_embeddings=514, type_vocab_size=1)),
+    "bert-large": ("bert", dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096)),
+    "bert": ("bert", dict()),
+}
+
+
+def build_hf_mlm(model_args):
+    from transformers import AutoConfig, AutoModelForMaskedLM
+    path = model_args.get("model_name_or_path", model_args["model_name"])
+    if isinstance(path, str) and os.path.isdir(path):
+        return AutoModelForMaskedLM.from_pretrained(path, local_files_only=True)
+    name = str(model_args["model_name"]).lower()
+    for frag, (mtype, over) in _ARCH.items():
+        if frag in name:
+            over = dict(over, **(model_args.get("config_overrides", {}) or {}))
+            cfg = AutoConfig.for_model(mtype, **over)
+            cfg._attn_implementation = "sdpa"
+            return AutoModelForMaskedLM.from_config(cfg)
+    raise ValueError("unknown architecture {!r}: give a local model_name_or_path".format(model_args["model_name"]))
+
+
+class LabelSmoother:
+    """NLL with uniform label smoothing over the vocabulary, ignoring ``ignore_index`` positions."""
+
+    def __init__(self, epsilon=0.1, ignore_index=-100):
+        self.epsilon, self.ignore_index = epsilon, ignore_index
+
+    def __call__(self, model_output, labels):
+        logits = model_output["logits"] if isinstance(model_output, dict) else model_output[0]
+        logp = -T.nn.functional.log_softmax(logits.float(), dim=-1)
+        labels = labels.to(logits.device)
+        pad = labels.eq(self.ignore_index)
+        nll = logp.gather(-1, labels.clamp(min=0).unsqueeze(-1)).squeeze(-1).masked_fill(pad, 0.0)
+        smooth = logp.sum(-1).masked_fill(pad, 0.0)
+        n = (~pad).sum().clamp(min=1)
+        return (1 - self.epsilon) * nll.sum() / n + self.epsilon * smooth.sum() / (n * logits.shape[-1])
+
+
+class BERT(BaseModel):
+    def __init__(self, model_config, **kwargs):
+        super().__init__()
+        args = model_config["BERT"]
+        model_args, training_args = args["model"], args.get("training", {}) or {}
+        T.manual_seed(int(training_args.get("seed", 12345)))
+        self.gradient_accumulation_steps = model_args.get("gradient_accumulation_steps", 1)
+        self.batch_size = training_args.get("batch_size", 8)
+        self.model_name = model_args["model_name"]
+        eps = training_args.get("label_smoothing_factor", 0) or 0
+        self.label_smoother = LabelSmoother(eps) if eps != 0 else None
+        self.model = build_hf_mlm(model_args)
+        vocab = model_args.get("vocab_size", None)
+        if vocab:
+            self.model.resize_token_embeddings(int(vocab))
+        if model_args.get("adapter", False) and hasattr(self.model, "add_adapter"):
+            self.model.add_adapter("FLUTE")
+            self.model.train_adapter("FLUTE")
+        self.tc_layers = 0
+        if model_args.get("tcgen05_linear", True):
+            from ..ops.linear_ops import swap_linear_modules
+            # encoder GEMMs (QKV / attention-out / FFN) → hand-written tcgen05 kernel; the tied vocabulary
+            # decoder keeps its own module (weight tying is implemented by HF on that specific attribute)
+            enc = getattr(self.model, "bert", None) or getattr(self.model, "roberta", None)
+            if enc is not None:
+                self.tc_layers = swap_linear_modules(enc)
+        n = sum(p.numel() for p in self.model.parameters())
+        print_rank("mlm_bert: {} with {:.1f}M parameters".format(self.model_name, n / 1e6), logging.INFO)
+
+    def get_model(self):
+        return self.model
+
+    def _prepare_inputs(self, inputs):
+        dev = next(self.model.parameters()).device
+        out = {k: (v.to(dev, non_blocking=True) if isinstance(v, T.Tensor) else v) for k, v in inputs.items()
+               if k in ("input_ids", "attention_mask", "token_type_ids", "labels", "special_tokens_mask", "position_ids")}
+        out.pop("special_tokens_mask", None)
+        if "roberta" in str(self.model_name).lower():
+            out.pop("attention_mask", None)
+        return out
+
+    def forward(self, inputs):
+        return self.model(**self._prepare_inputs(inputs))
+
+    def compute_loss(self, inputs, return_outputs=False):
+        inputs = self._prepare_inputs(inputs)
+        labels = inputs["labels"] if self.label_smoother is not None and "labels" in inputs else None
+        outputs = self.model(**inputs)
+        loss = self.label_smoother(outputs, labels) if labels is not None else outputs["loss"]
+        return (loss, outputs) if return_outputs else loss
+
+    def loss(self, inputs):
+        return self.compute_loss(inputs) / self.gradient_accumulation_steps
+
+    @staticmethod
+    def masked_accuracy(logits, labels):
+        mask = labels != -100
+        hit = (logits.argmax(-1) == labels) & mask
+        return hit.sum().float() / mask.sum().clamp(min=1)
+
+    def loss_and_metrics(self, inputs):
+        self.model.eval()
+        with T.no_grad():
+            loss, outputs = self.compute_loss(inputs, return_outputs=True)
+            labels = inputs["labels"].to(outputs["logits"].device)
+            acc = self.masked_accuracy(outputs["logits"], labels)
+        return loss.mean().detach(), {"output": None, "acc": acc, "batch_size": int(labels.shape[0])}
+
+    def inference(self, inputs, ignore_keys=None, metric_key_prefix="eval"):
+        loss, m = self.loss_and_metrics(inputs)
+        return {"output": loss.item(), "acc": m["acc"].item(), "batch_size": m["batch_size"]}
