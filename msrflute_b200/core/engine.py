@@ -66,6 +66,22 @@ class _Slot:
         self.kernels_per_replay: Dict[tuple, int] = {}
 
 
+class DeferredRound:
+    """Handle for a round whose GPU work is enqueued but whose per-client records have not been read back yet."""
+
+    def __init__(self, n_clients, weight_sum, resolve):
+        self.n_clients = n_clients
+        self.weight_sum = weight_sum          # device scalar: Σ aggregation weights (what the fused update divides by)
+        self._resolve = resolve
+        self._outs = None
+
+    def resolve(self):
+        if self._outs is None:
+            self._outs = self._resolve()
+            self._resolve = None
+        return self._outs
+
+
 class DeviceClientEngine:
     @staticmethod
     def maybe_create(worker, config, task):
@@ -168,6 +184,7 @@ class DeviceClientEngine:
                 print_rank("device engine: slot-batched hand-written conv/GroupNorm path enabled", logging.INFO)
         self.wave_graphs: Dict[tuple, object] = {}
         self.wave_static: Dict[tuple, dict] = {}
+        self._staging: Dict[tuple, list] = {}
         self.wave_kernels: Dict[tuple, int] = {}
         self.wave_pool = None
         self._built = True
@@ -334,7 +351,11 @@ class DeviceClientEngine:
         return True
 
     # ------------------------------------------------------------------ a round's share
-    def train_clients(self, client_ids, lr, nround, w_global, acc):
+    def train_clients(self, client_ids, lr, nround, w_global, acc, defer=False):
+        """Train ``client_ids`` (all enqueued, no host sync inside).  ``defer=True`` returns a :class:`DeferredRound`:
+        the per-client record table is copied to pinned memory asynchronously and only read when the caller
+        ``resolve()``s it — the server enqueues its fused update / checkpoint snapshot first, so the host work of a
+        round overlaps the GPU instead of following it."""
         if not self._built:
             self._build()
         cfg = self.config
@@ -435,20 +456,46 @@ class DeviceClientEngine:
             rec[:, REC_SUM:REC_COUNT + 1] = self.stats[:n_act, 0:3]
             rec[:, REC_NS] = ns_t[:n_act]
             rec[:, REC_WEIGHT] = self.weights[:n_act]
-        host = records.cpu().numpy().astype(np.float64)              # the round's single device→host read
         self.d2h_bytes_last_round = records.numel() * records.element_size()
-        t_end = time.time()
-        per = (t_end - t_begin) / max(len(client_ids), 1)
-        outs = []
-        for i, cid in enumerate(client_ids):
-            r = host[i]
-            n = max(r[REC_COUNT], 1.0)
-            mag = math.sqrt(max(r[REC_SUMSQ], 0.0) / n)
-            outs.append({
-                "cs": {"setup": 0.0, "training": per, "full cost": per},
-                "tl": float(r[REC_LOSS]), "mg": np.float32(mag), "vg": np.float32(r[REC_SUMSQ] / n - mag * mag),
-                "ng": np.float32(r[REC_SUM] / n), "rg": np.float32(math.sqrt(max(r[REC_SUMSQ], 0.0))),
-                "ns": int(r[REC_NS]), "pl": {"weight": float(r[REC_WEIGHT]), "gradients": None, "fused": True},
-                "ts": t_end,
-            })
-        return outs
+        n_clients = len(client_ids)
+
+        def build(host):
+            t_end = time.time()
+            per = (t_end - t_begin) / max(n_clients, 1)
+            outs = []
+            for i in range(n_clients):
+                r = host[i]
+                n = max(r[REC_COUNT], 1.0)
+                mag = math.sqrt(max(r[REC_SUMSQ], 0.0) / n)
+                outs.append({
+                    "cs": {"setup": 0.0, "training": per, "full cost": per},
+                    "tl": float(r[REC_LOSS]), "mg": np.float32(mag), "vg": np.float32(r[REC_SUMSQ] / n - mag * mag),
+                    "ng": np.float32(r[REC_SUM] / n), "rg": np.float32(math.sqrt(max(r[REC_SUMSQ], 0.0))),
+                    "ns": int(r[REC_NS]), "pl": {"weight": float(r[REC_WEIGHT]), "gradients": None, "fused": True},
+                    "ts": t_end,
+                })
+            return outs
+
+        if defer and dev.type == "cuda":
+            pinned = self._record_staging(records.shape)
+            pinned.copy_(records, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            wsum = records[:, REC_WEIGHT].sum()
+
+            def resolve():
+                ev.synchronize()                                         # the round's single device→host read
+                return build(pinned.numpy().astype(np.float64))
+
+            return DeferredRound(n_clients, wsum, resolve)
+        return build(records.cpu().numpy().astype(np.float64))          # the round's single device→host read
+
+    def _record_staging(self, shape):
+        """Two alternating pinned buffers (a deferred round may still be unread when the next one is enqueued)."""
+        key = tuple(shape)
+        ring = self._staging.setdefault(key, [])
+        if len(ring) < 2:
+            ring.append(torch.empty(key, dtype=torch.float32).pin_memory())
+            return ring[-1]
+        ring.append(ring.pop(0))
+        return ring[-1]

@@ -155,12 +155,13 @@ class Server:
 
     @staticmethod
     def dispatch_clients(clients, server_data, command, mode=None, do_profiling=False, single_worker=None,
-                         costs=None, fused=False, sync_weights=True, extra=None):
+                         costs=None, fused=False, sync_weights=True, extra=None, defer=False):
         """Run ``command`` for ``clients`` on the available workers; generator of per-client outputs.
 
         ``server_data`` = ``(lr, weights, round)`` where ``weights`` is the server's flat arena tensor (fast path),
-        a list of tensors (reference format) or None (keep what workers already hold).  In ``fused`` TRAIN mode the
-        outputs carry ``pl = {'weight', 'gradients': None, 'fused': True}`` and the weighted pseudo-gradient sum
+        a list of tensors (reference format) or None (keep what workers already hold).  ``defer`` (single-process
+        fused training on the device engine) yields ONE :class:`~.engine.DeferredRound` instead of per-client
+        dicts: nothing has been read back from the GPU yet.  In ``fused`` TRAIN mode the outputs carry ``pl = {'weight', 'gradients': None, 'fused': True}`` and the weighted pseudo-gradient sum
         ends up in the server worker's accumulator (see :meth:`take_accumulator`)."""
         comm = get_comm()
         worker = single_worker or _Runtime.worker
@@ -188,7 +189,11 @@ class Server:
         if worker is not None and assign.get(comm.rank if comm.size > 1 else 0):
             mine = assign[comm.rank if comm.size > 1 else 0]
             if command == COMMAND_TRAIN:
-                local_out = worker.train_clients(mine, (lr, None, nround), fused=fused, extra=ctrl["extra"])
+                local_out = worker.train_clients(mine, (lr, None, nround), fused=fused, extra=ctrl["extra"],
+                                                 defer=defer and comm.size == 1)
+                if not isinstance(local_out, list):          # DeferredRound
+                    yield local_out
+                    return
             else:
                 local_out = worker.eval_clients(mine, mode, (lr, None, nround))
         for o in local_out:
@@ -322,7 +327,7 @@ class Worker:
         return self._weights_list if self._weights_list is not None else self.weight_buffer()
 
     # ---- work ---------------------------------------------------------------
-    def train_clients(self, client_ids, server_data, fused=False, extra=None):
+    def train_clients(self, client_ids, server_data, fused=False, extra=None, defer=False):
         lr, _, nround = server_data
         cfg = self.config
         if extra:
@@ -331,7 +336,8 @@ class Worker:
             if extra.get("max_allowed_leakage") is not None:
                 cfg["privacy_metrics_config"]["max_allowed_leakage"] = extra["max_allowed_leakage"]
         if self.engine is not None and fused and self.engine.supports(cfg):
-            return self.engine.train_clients(client_ids, lr, nround, self._server_weights(), self.accumulator())
+            return self.engine.train_clients(client_ids, lr, nround, self._server_weights(), self.accumulator(),
+                                             defer=defer)
         outs = []
         send_grads = cfg["client_config"].get("type", "gradient_computation") == "optimization"
         profiler = None

@@ -35,8 +35,10 @@ from ..parallel.arena import adopt_module, module_arena
 from ..utils import get_lr, print_rank, to_device, update_json_log
 from ..utils.metrics_sink import get_run
 from . import federated
+from .engine import DeferredRound
 from .evaluation import Evaluation
 from .strategies import select_strategy
+from . import trainer as _trainer_mod
 from .trainer import ModelUpdater, Trainer, set_component_wise_lr
 
 run = get_run()
@@ -231,11 +233,13 @@ class OptimizationServer(federated.Server):
         log_metric("Current iteration", i)
         initial_lr = self.initial_lr_client * self.lr_weight
         print_rank("Client learning rate {}".format(initial_lr), logging.DEBUG)
-        self.worker_trainer.optimizer.zero_grad(set_to_none=False) if self.worker_trainer.optimizer is not None \
-            else self.worker_trainer.model.zero_grad()
         ar = module_arena(self.worker_trainer.model)
         if ar is not None and ar[1] is not None:
-            ar[1].zero_()
+            ar[1].zero_()                 # every .grad is a view of the flat gradient arena: one memset
+        elif self.worker_trainer.optimizer is not None:
+            self.worker_trainer.optimizer.zero_grad(set_to_none=False)
+        else:
+            self.worker_trainer.model.zero_grad()
         self.train_loss = []
         server_data = (initial_lr, self._global_weights(), i)
 
@@ -278,8 +282,8 @@ class OptimizationServer(federated.Server):
         fused_weights = []
         in_sync = fused and getattr(self, "_weights_in_sync", False)
         self._weights_in_sync = False
-        for client_output in self.process_clients(sampled_idx_clients, server_data, self.single_worker,
-                                                  costs=costs, fused=fused, extra=extra, sync_weights=not in_sync):
+        def consume(client_output):
+            nonlocal num_clients_curr_iter
             client_stats = client_output["cs"]
             client_payload = client_output["pl"]
             if apply_privacy_metrics and "ps" in client_output:
@@ -297,7 +301,7 @@ class OptimizationServer(federated.Server):
             if not processed:
                 print_rank("Dropping client", loglevel=logging.DEBUG)
                 num_clients_curr_iter -= 1
-                continue
+                return
             self.train_loss.append(client_output["tl"])
             client_mag_grads.append(float(client_output["mg"]))
             client_mean_grads.append(float(client_output["ng"]))
@@ -309,8 +313,27 @@ class OptimizationServer(federated.Server):
             self.run_stats["secsPerClientSetup"][-1].append(client_stats["setup"])
             self.run_stats["secsPerClient"][-1].append(client_end - clients_begin)
 
+        # Deferred read-back (device engine, single process): the clients' GPU work is only ENQUEUED here; the fused
+        # server update, LR schedule and checkpoint snapshot are enqueued behind it and the per-client records are
+        # read at the end of the round, so this round's host work overlaps its GPU work.
+        deferred = None
+        can_defer = fused and self._can_defer(apply_privacy_metrics)
+        for client_output in self.process_clients(sampled_idx_clients, server_data, self.single_worker, costs=costs,
+                                                  fused=fused, extra=extra, sync_weights=not in_sync, defer=can_defer):
+            if isinstance(client_output, DeferredRound):
+                deferred = client_output
+                continue
+            consume(client_output)
+
         fused_done = False
-        if fused:
+        if fused and deferred is not None:
+            fused_done = self._fused_server_update(None, i, num_clients_curr_iter, log_metric, wsum=deferred.weight_sum)
+            if not fused_done:
+                for o in deferred.resolve():
+                    consume(o)
+                deferred = None
+                self._install_fused_aggregate(fused_weights)
+        elif fused:
             fused_done = self._fused_server_update(fused_weights, i, num_clients_curr_iter, log_metric)
             if not fused_done:
                 self._install_fused_aggregate(fused_weights)
@@ -336,7 +359,8 @@ class OptimizationServer(federated.Server):
         end = time.time()
         self.run_stats["secsPerClientRound"].append(end - begin)
         begin = end
-        log_metric("Training loss", sum(self.train_loss))
+        if deferred is None:
+            log_metric("Training loss", sum(self.train_loss))
 
         if not fused_done:
             self.losses = self.strategy.combine_payloads(
@@ -381,8 +405,13 @@ class OptimizationServer(federated.Server):
             from ..utils.async_ckpt import flush_checkpoints
             flush_checkpoints()         # the epoch<i>_best_* copies below read files back
         self.fall_back_to_prev_best_status()
+        if deferred is not None:                       # everything of this round is enqueued: now read the records
+            for o in deferred.resolve():
+                consume(o)
+            log_metric("Training loss", sum(self.train_loss))
+        bg = _trainer_mod.ASYNC_CHECKPOINTS["enabled"]
         if len(self.metrics) > 1:
-            update_json_log(self.log_path, {
+            update_json_log(self.log_path, background=bg, status_info={
                 "i": i + 1,
                 "best_val_loss": float(self.metrics.get("best_val_loss", float("inf"))),
                 "best_val_acc": float(self.metrics.get("best_val_acc", 0)),
@@ -392,8 +421,8 @@ class OptimizationServer(federated.Server):
                 "num_label_updates": int(self.no_label_updates),
             })
         else:
-            update_json_log(self.log_path, {"i": i + 1, "weight": float(self.lr_weight),
-                                            "num_label_updates": int(self.no_label_updates)})
+            update_json_log(self.log_path, background=bg, status_info={
+                "i": i + 1, "weight": float(self.lr_weight), "num_label_updates": int(self.no_label_updates)})
         end = time.time()
         self.run_stats["secsPerRoundHousekeeping"].append(end - begin)
         self.run_stats["secsPerRoundTotal"].append(
@@ -413,11 +442,18 @@ class OptimizationServer(federated.Server):
         for hook in self.round_hooks:
             hook(i, metrics_payload)
 
-    def _fused_server_update(self, weights, curr_iter, num_clients_curr_iter, log_metric):
+    def _can_defer(self, apply_privacy_metrics):
+        """Deferred read-back needs a round whose server side never looks at per-client host values."""
+        dp = self.config.get("dp_config", None) or {}
+        return (torch.cuda.is_available() and not apply_privacy_metrics and not self.do_profiling
+                and not dp.get("enable_global_dp", False) and not self.config.get("dump_norm_stats", False)
+                and not self.strategy.skip_model_update and federated.get_comm().size == 1)
+
+    def _fused_server_update(self, weights, curr_iter, num_clients_curr_iter, log_metric, wsum=None):
         """Fast path: the weighted pseudo-gradient sums (already reduced onto this rank, or peer-mapped when the
         transport is symmetric memory) go through ONE fused reduce/normalise/DP/optimizer/broadcast kernel
         (``ModelUpdater.fused_update``).  Returns False when some option needs the generic strategy path."""
-        if not torch.cuda.is_available() or not weights or self.strategy.skip_model_update:
+        if not torch.cuda.is_available() or (wsum is None and not weights) or self.strategy.skip_model_update:
             return False
         if self.config.get("dump_norm_stats", False):
             return False
@@ -431,7 +467,8 @@ class OptimizationServer(federated.Server):
             noise_scale = dp["global_sigma"] * dp["max_grad"] / num_clients_curr_iter
             seed = (int(self.config["server_config"].get("b200", {}).get("seed", 0)) << 32) ^ (curr_iter + 1)
             stats_out = torch.zeros(2, device=worker.accumulator().device)
-        wsum = torch.tensor(float(sum(weights)), device=worker.accumulator().device)
+        if wsum is None:
+            wsum = torch.tensor(float(sum(weights)), device=worker.accumulator().device)
         accs = comm.peer_accumulators(worker.accumulator()) if hasattr(comm, "peer_accumulators") \
             else [worker.accumulator()]
         bcast = comm.peer_weight_buffers(worker.weight_buffer()) if hasattr(comm, "peer_weight_buffers") else None

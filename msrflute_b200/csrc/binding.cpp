@@ -46,6 +46,7 @@ at::Tensor slot_conv_dgrad(at::Tensor dy, at::Tensor w_arena, int64_t w_offset, 
                            int64_t KH, int64_t KW, int64_t stride, int64_t pad);
 void slot_conv_wgrad(at::Tensor x, at::Tensor dy, at::Tensor g_arena, int64_t g_offset, int64_t KH, int64_t KW,
                      int64_t stride, int64_t pad);
+void slot_conv_set_impl(int64_t impl);
 }  // namespace flute
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -67,6 +68,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("slot_conv_fprop", &flute::slot_conv_fprop);
   m.def("slot_conv_dgrad", &flute::slot_conv_dgrad);
   m.def("slot_conv_wgrad", &flute::slot_conv_wgrad);
+  m.def("slot_conv_set_impl", &flute::slot_conv_set_impl);
   m.def("gru_cell_fwd", &flute::gru_cell_fwd);
   m.def("gru_cell_bwd", &flute::gru_cell_bwd);
   m.def("lstm_cell_fwd", &flute::lstm_cell_fwd);

@@ -25,6 +25,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/types.h>
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace flute {
 namespace conv {
@@ -345,6 +346,311 @@ static void check_arena(const at::Tensor& a, int64_t S) {
               "arena must be a contiguous fp32 CUDA [S, P] tensor");
 }
 
+
+// ====================================================================================================================
+// tcgen05 path: the same three implicit GEMMs on the 5th-generation tensor cores (kind::tf32, fp32 accumulate in TMEM).
+//
+// The operand tiles of a convolution are gathers (im2col with padding / stride / pruned taps, and weights that live
+// inside the parameter arena in [Cout, Cin, KH, KW] order), so TMA cannot fetch them from NCHW tensors; instead eight
+// PRODUCER warps gather 128 x 32 (A) and 64 x 32 (B) fp32 tiles straight into the K-major SWIZZLE_128B shared-memory
+// layout that tcgen05.mma consumes, fence them to the async proxy and arrive on the stage's mbarrier.  One elected
+// thread of warp 8 issues four UMMA 128x64x8 per stage and releases the stage with tcgen05.commit; after the last stage
+// the producer warps become the epilogue: tcgen05.ld the fp32 accumulator (thread == tile row) and scatter it to NCHW /
+// the gradient arena (plain stores, or fp32 atomics when the reduction is split over blockIdx.z).
+//
+// Versus the FMA kernels above this removes the 256 FMAs + 32 LDS.128 per thread per 16-deep chunk (the tensor core does
+// a 128x64x32 stage asynchronously) and decodes each reduction index once per row instead of once per element:
+//   * "row" gathers   (fprop/dgrad A): thread == tile row (output pixel), walks 16 reduction indices (ci, tap) with an
+//     incremental decode; consecutive threads read consecutive pixels (coalesced) and write one 16-byte chunk each;
+//   * "lane" gathers  (weights, and both wgrad operands): lane == reduction index (contiguous in memory), loop over
+//     tile rows; a warp writes one full 128-byte swizzled row per store (bank-conflict free).
+namespace tcv {
+using namespace tc;
+
+constexpr int TM = 128, TN = 64, TK = 32, T_UMMA_K = 8, T_STAGES = 4;
+constexpr int T_PRODUCERS = 256, T_THREADS = 288;
+constexpr int T_A_BYTES = TM * TK * 4, T_B_BYTES = TN * TK * 4, T_STAGE_BYTES = T_A_BYTES + T_B_BYTES;
+constexpr int T_TABLE_BYTES = TM * 8 + 64 * 8;             // wgrad row table + per-tap (offset, dh, dw) table
+constexpr int T_SMEM = T_STAGES * T_STAGE_BYTES + T_TABLE_BYTES + 256 + 1024;
+enum { FPROP = 0, DGRAD = 1, WGRAD = 2 };
+
+__device__ __forceinline__ void st_elem(uint8_t* tile, int row, int e, float v) {     // element e (0..31) of a tile row
+  *reinterpret_cast<float*>(tile + sw128_offset(row, e >> 2) + (e & 3) * 4) = v;
+}
+
+// in0/in1/out per mode:  FPROP: x, w, y   DGRAD: dy, w, dx   WGRAD: x, dy, dw(grad arena, accumulated)
+template <int MODE>
+__global__ void __launch_bounds__(T_THREADS, 2)
+conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out, const ConvP p,
+               const int vec_b) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  int2* row_table = reinterpret_cast<int2*>(smem + T_STAGES * T_STAGE_BYTES);
+  int2* tap_table = row_table + TM;                  // [ntaps] {kh * W + kw, kh << 16 | kw}: no LDC / branches in the gathers
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T_STAGES * T_STAGE_BYTES + T_TABLE_BYTES);
+  uint64_t* empty_bar = full_bar + T_STAGES;
+  uint64_t* acc_bar = empty_bar + T_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slot = blockIdx.z / p.splits, split = blockIdx.z - slot * p.splits;
+  const int KHW = p.KH * p.KW, HiWi = p.Hi * p.Wi, HoWo = p.Ho * p.Wo;
+  // GEMM view of this mode: R rows x C cols, reduction length RED
+  const int R = MODE == FPROP ? p.B * HoWo : MODE == DGRAD ? p.B * HiWi : p.Cin * p.ntaps;
+  const int C = MODE == FPROP ? p.Cout : MODE == DGRAD ? p.Cin : p.Cout;
+  const int RED = MODE == FPROP ? p.Cin * p.ntaps : MODE == DGRAD ? p.Cout * p.ntaps : p.B * HoWo;
+  const int r_tile0 = blockIdx.x * TM, c_tile0 = blockIdx.y * TN;
+  const int stages_total = (RED + TK - 1) / TK;
+  const int per = (stages_total + p.splits - 1) / p.splits;
+  const int st_begin = split * per, st_end = min(stages_total, st_begin + per);
+  const int nst = max(0, st_end - st_begin);
+
+  if (tid == 0) {
+    for (int s = 0; s < T_STAGES; ++s) {
+      mbar_init(full_bar + s, T_PRODUCERS);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_ptr, TN);
+  if (tid >= TM && tid < TM + p.ntaps) {
+    const int t = p.taps[tid - TM], kh = t >> 8, kw = t & 255;
+    tap_table[tid - TM] = make_int2(kh * (MODE == DGRAD ? p.Wo : p.Wi) + kw, (kh << 16) | kw);
+  }
+  if (MODE == WGRAD && tid < TM) {                   // per-row (ci, tap) decode of this tile, shared by all stages
+    const int k = r_tile0 + tid;
+    int2 e = make_int2(0, 0x7F7F);                   // kh = kw = 127: always out of bounds -> zero row
+    if (k < R) {
+      const int ci = k / p.ntaps, t = p.taps[k - ci * p.ntaps];
+      e = make_int2(ci * HiWi + (t >> 8) * p.Wi + (t & 255), t);
+    }
+    row_table[tid] = e;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const long long in0_slot = static_cast<long long>(slot) * p.B * (MODE == DGRAD ? p.Cout * HoWo : p.Cin * HiWi);
+  const float* a_src = in0 + in0_slot;                                           // x (fprop/wgrad) or dy (dgrad)
+  const float* b_src = MODE == WGRAD ? in1 + static_cast<long long>(slot) * p.B * p.Cout * HoWo      // dy
+                                     : in1 + static_cast<long long>(slot) * p.w_slot_stride;         // weights
+
+  if (tid < T_PRODUCERS) {
+    // ------------------------------------------------------------------------------------------ producers
+    const int row = tid & (TM - 1), khalf = tid >> 7;
+    // row-gather state (fprop / dgrad): this thread's output pixel
+    bool rvalid = false;
+    int base = 0, h0 = 0, w0 = 0;
+    const int sshift = p.stride == 1 ? 0 : p.stride == 2 ? 1 : p.stride == 4 ? 2 : -1;
+    if (MODE == FPROP) {
+      const int m = r_tile0 + row;
+      if (m < R) {
+        const int b = m / HoWo, r = m - b * HoWo, oh = r / p.Wo, ow = r - oh * p.Wo;
+        rvalid = true; base = b * p.Cin * HiWi; h0 = oh * p.stride - p.pad; w0 = ow * p.stride - p.pad;
+      }
+    } else if (MODE == DGRAD) {
+      const int m = r_tile0 + row;
+      if (m < R) {
+        const int b = m / HiWi, r = m - b * HiWi, ih = r / p.Wi, iw = r - ih * p.Wi;
+        rvalid = true; base = b * p.Cout * HoWo; h0 = ih + p.pad; w0 = iw + p.pad;
+      }
+    }
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % T_STAGES;
+      mbar_wait(empty_bar + s, ((it / T_STAGES) & 1) ^ 1);
+      uint8_t* sa = smem + s * T_STAGE_BYTES;
+      uint8_t* sb = sa + T_A_BYTES;
+      const int r0 = (st_begin + it) * TK;
+      if (MODE == FPROP || MODE == DGRAD) {
+        // ---- A: row gather, 16 reduction indices of this thread's pixel.  Branch-free: out-of-range elements load
+        // element 0 and are zeroed by a select, so all 16 loads are in flight together.
+        const int k = r0 + khalf * 16;
+        const int c0 = k / p.ntaps;                         // ci (fprop) / co (dgrad) of the first index
+        int ti = k - c0 * p.ntaps;
+        int cbase = base + c0 * (MODE == FPROP ? HiWi : HoWo);
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int2 tp = tap_table[ti];
+          const int kh = tp.y >> 16, kw = tp.y & 0xFFFF;
+          bool ok = rvalid && (k + j < RED);
+          int idx;
+          if (MODE == FPROP) {
+            const int ih = h0 + kh, iw = w0 + kw;
+            ok = ok && static_cast<unsigned>(ih) < static_cast<unsigned>(p.Hi) && static_cast<unsigned>(iw) < static_cast<unsigned>(p.Wi);
+            idx = cbase + ih * p.Wi + iw;
+          } else {
+            const int th = h0 - kh, tw = w0 - kw;           // = oh * stride, ow * stride
+            int oh, ow;
+            if (sshift >= 0) {
+              ok = ok && (((th | tw) & (p.stride - 1)) == 0);
+              oh = th >> sshift; ow = tw >> sshift;         // negative th/tw stay negative -> fail the unsigned compare
+            } else {
+              oh = th / p.stride; ow = tw / p.stride;
+              ok = ok && th >= 0 && tw >= 0 && oh * p.stride == th && ow * p.stride == tw;
+            }
+            ok = ok && static_cast<unsigned>(oh) < static_cast<unsigned>(p.Ho) && static_cast<unsigned>(ow) < static_cast<unsigned>(p.Wo);
+            idx = cbase + oh * p.Wo + ow;
+          }
+          const float xv = __ldg(a_src + (ok ? idx : 0));
+          v[j] = ok ? xv : 0.f;
+          const bool wrap = ++ti == p.ntaps;
+          ti = wrap ? 0 : ti;
+          cbase += wrap ? (MODE == FPROP ? HiWi : HoWo) : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(sa + sw128_offset(row, khalf * 4 + q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        // ---- B: weights
+        if (MODE == FPROP && vec_b) {
+          // unpruned filter with a 16-byte aligned row pitch: the reduction index IS the memory index
+          const int chunk = tid & 7;
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            const int brow = (tid >> 3) + pass * 32, n = c_tile0 + brow, kk = r0 + chunk * 4;
+            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < C && kk < RED) wv = __ldg(reinterpret_cast<const float4*>(b_src + static_cast<long long>(n) * RED + kk));
+            *reinterpret_cast<float4*>(sb + sw128_offset(brow, chunk)) = wv;
+          }
+        } else {
+          const int kb = r0 + lane;
+          long long woff = -1;
+          if (kb < RED) {
+            const int cc = kb / p.ntaps;
+            const int2 tp = tap_table[kb - cc * p.ntaps];
+            const int tap_off = (tp.y >> 16) * p.KW + (tp.y & 0xFFFF);
+            woff = MODE == FPROP ? static_cast<long long>(cc) * KHW + tap_off
+                                 : static_cast<long long>(cc) * p.Cin * KHW + tap_off;
+          }
+          const long long row_pitch = MODE == FPROP ? static_cast<long long>(p.Cin) * KHW : KHW;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int brow = warp * 8 + i, n = c_tile0 + brow;
+            const bool okb = woff >= 0 && n < C;
+            const float wv = __ldg(b_src + (okb ? woff + n * row_pitch : 0));
+            st_elem(sb, brow, lane, okb ? wv : 0.f);
+          }
+        }
+      } else {
+        // ---- wgrad: lane == output pixel m (contiguous in both x and dy), loop over tile rows
+        const int m = r0 + lane;
+        const bool mv = m < RED;
+        int xpart = 0, dypart = 0, ihb = 0, iwb = 0;
+        if (mv) {
+          const int b = m / HoWo, r = m - b * HoWo, oh = r / p.Wo, ow = r - oh * p.Wo;
+          ihb = oh * p.stride - p.pad; iwb = ow * p.stride - p.pad;
+          xpart = b * p.Cin * HiWi + ihb * p.Wi + iwb;
+          dypart = b * p.Cout * HoWo + r;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int arow = warp * 16 + i;
+          const int2 e = row_table[arow];
+          const int ih = ihb + (e.y >> 8), iw = iwb + (e.y & 255);
+          const bool ok = mv && static_cast<unsigned>(ih) < static_cast<unsigned>(p.Hi) && static_cast<unsigned>(iw) < static_cast<unsigned>(p.Wi);
+          const float xv = __ldg(a_src + (ok ? xpart + e.x : 0));
+          st_elem(sa, arow, lane, ok ? xv : 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int brow = warp * 8 + i, co = c_tile0 + brow;
+          const bool okd = mv && co < C;
+          const float dv = __ldg(b_src + (okd ? dypart + co * HoWo : 0));
+          st_elem(sb, brow, lane, okd ? dv : 0.f);
+        }
+      }
+      fence_proxy_async();                           // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(full_bar + s);
+    }
+    // ------------------------------------------------------------------------------------------ epilogue
+    if (nst > 0) {
+      mbar_wait(acc_bar, 0);
+      tc_fence_after();
+      const int q = warp & 3, chalf = warp >> 2;     // TMEM lane quadrant of this warp, 32-column half
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(chalf * 32), v);
+      const int rr = r_tile0 + q * 32 + lane;
+      if (rr < R) {
+        if (MODE == WGRAD) {
+          const int ci = rr / p.ntaps, t = p.taps[rr - ci * p.ntaps];
+          float* dst = out + static_cast<long long>(slot) * p.w_slot_stride + ci * KHW + (t >> 8) * p.KW + (t & 255);
+          const long long pitch = static_cast<long long>(p.Cin) * KHW;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int co = c_tile0 + chalf * 32 + j;
+            if (co < C) atomicAdd(dst + co * pitch, __uint_as_float(v[j]));
+          }
+        } else {
+          const int HW = MODE == FPROP ? HoWo : HiWi;
+          const int b = rr / HW, r = rr - b * HW;
+          float* dst = out + (static_cast<long long>(slot) * p.B + b) * C * HW + r;
+          const int n_base = c_tile0 + chalf * 32;
+          dst += static_cast<long long>(n_base) * HW;
+          if (p.splits > 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n_base + j < C) atomicAdd(dst + j * HW, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n_base + j < C) dst[j * HW] = __uint_as_float(v[j]);
+          }
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_fmt(TM, TN, 2u);
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % T_STAGES;
+      mbar_wait(full_bar + s, (it / T_STAGES) & 1);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + s * T_STAGE_BYTES);
+      const uint64_t adesc = make_smem_desc(a_addr), bdesc = make_smem_desc(a_addr + T_A_BYTES);
+#pragma unroll
+      for (int k = 0; k < TK / T_UMMA_K; ++k)         // 8 tf32 = 32 bytes along K: +2 in the (addr >> 4) field
+        umma_tf32(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                  (it | k) != 0 ? 1u : 0u);
+      umma_commit(empty_bar + s);
+    }
+    if (nst > 0) umma_commit(acc_bar);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TN);
+  }
+}
+
+static int pick_splits_tc(long long tiles, int stages) {
+  const long long target = 148LL * 2;              // two CTAs (2 x 98 KB smem, 2 x 64 TMEM columns) are resident per SM
+  if (tiles >= target || stages < 4) return 1;
+  long long s = (target + tiles - 1) / tiles;
+  s = std::min<long long>(s, stages / 2);
+  return static_cast<int>(std::max<long long>(1, std::min<long long>(s, 32)));
+}
+
+template <int MODE>
+static void launch_tc(const float* in0, const float* in1, float* out, const ConvP& p, int rows, int cols, int vec_b) {
+  static bool configured = false;
+  if (!configured) {
+    FLUTE_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
+    configured = true;
+  }
+  dim3 grid((rows + TM - 1) / TM, (cols + TN - 1) / TN, p.S * p.splits);
+  conv_tc_kernel<MODE><<<grid, T_THREADS, T_SMEM, at::cuda::getCurrentCUDAStream()>>>(in0, in1, out, p, vec_b);
+  FLUTE_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace tcv
+
+// 0 = auto (tcgen05 when the GEMM has >= 48 rows / reduction items per slot), 1 = FMA kernels only, 2 = tcgen05 always
+static int g_conv_impl = 0;
+static bool use_tc(int work_rows) { return g_conv_impl == 2 || (g_conv_impl == 0 && work_rows >= 48); }
+
 }  // namespace conv
 
 // w_arena: the [S, P] parameter arena; the layer's weight of slot s lives at w_arena + s*P + w_offset
@@ -356,6 +662,15 @@ at::Tensor slot_conv_fprop(at::Tensor x, at::Tensor w_arena, int64_t w_offset, i
   ConvP p = make_params(x.size(0), x.size(1), x.size(2), x.size(3), x.size(4), Cout, KH, KW, stride, pad, w_arena.size(1));
   const c10::cuda::CUDAGuard guard(x.device());
   const int M = p.B * p.Ho * p.Wo, K = p.Cin * p.ntaps;
+  if (use_tc(M)) {
+    const long long tiles = static_cast<long long>((M + tcv::TM - 1) / tcv::TM) * ((p.Cout + tcv::TN - 1) / tcv::TN) * p.S;
+    p.splits = tcv::pick_splits_tc(tiles, (K + tcv::TK - 1) / tcv::TK);
+    auto y = p.splits > 1 ? at::zeros({p.S, p.B, p.Cout, p.Ho, p.Wo}, x.options())
+                          : at::empty({p.S, p.B, p.Cout, p.Ho, p.Wo}, x.options());
+    const int vec_b = (p.ntaps == p.KH * p.KW) && (K % 4 == 0) && ((w_offset % 4) == 0) && (w_arena.size(1) % 4 == 0);
+    tcv::launch_tc<tcv::FPROP>(x.data_ptr<float>(), w_arena.data_ptr<float>() + w_offset, y.data_ptr<float>(), p, M, p.Cout, vec_b);
+    return y;
+  }
   dim3 grid((M + BM - 1) / BM, (p.Cout + BN - 1) / BN, 1);
   p.splits = pick_splits(static_cast<long long>(grid.x) * grid.y * p.S, (K + BK - 1) / BK);
   grid.z = p.S * p.splits;
@@ -376,6 +691,14 @@ at::Tensor slot_conv_dgrad(at::Tensor dy, at::Tensor w_arena, int64_t w_offset, 
   TORCH_CHECK(p.Ho == dy.size(3) && p.Wo == dy.size(4), "dy spatial size mismatch");
   const c10::cuda::CUDAGuard guard(dy.device());
   const int M = p.B * p.Hi * p.Wi, K = p.Cout * p.ntaps;
+  if (use_tc(M)) {
+    const long long tiles = static_cast<long long>((M + tcv::TM - 1) / tcv::TM) * ((p.Cin + tcv::TN - 1) / tcv::TN) * p.S;
+    p.splits = tcv::pick_splits_tc(tiles, (K + tcv::TK - 1) / tcv::TK);
+    auto dx = p.splits > 1 ? at::zeros({p.S, p.B, p.Cin, p.Hi, p.Wi}, dy.options())
+                           : at::empty({p.S, p.B, p.Cin, p.Hi, p.Wi}, dy.options());
+    tcv::launch_tc<tcv::DGRAD>(dy.data_ptr<float>(), w_arena.data_ptr<float>() + w_offset, dx.data_ptr<float>(), p, M, p.Cin, 0);
+    return dx;
+  }
   dim3 grid((M + BM - 1) / BM, (p.Cin + BN - 1) / BN, 1);
   p.splits = pick_splits(static_cast<long long>(grid.x) * grid.y * p.S, (K + BK - 1) / BK);
   grid.z = p.S * p.splits;
@@ -399,12 +722,23 @@ void slot_conv_wgrad(at::Tensor x, at::Tensor dy, at::Tensor g_arena, int64_t g_
   TORCH_CHECK(p.Ho == dy.size(3) && p.Wo == dy.size(4), "dy spatial size mismatch");
   const c10::cuda::CUDAGuard guard(x.device());
   const int M = p.B * p.Ho * p.Wo, K = p.Cin * p.ntaps;
+  if (use_tc(M)) {
+    const long long tiles = static_cast<long long>((K + tcv::TM - 1) / tcv::TM) * ((p.Cout + tcv::TN - 1) / tcv::TN) * p.S;
+    p.splits = tcv::pick_splits_tc(tiles, (M + tcv::TK - 1) / tcv::TK);
+    tcv::launch_tc<tcv::WGRAD>(x.data_ptr<float>(), dy.data_ptr<float>(), g_arena.data_ptr<float>() + g_offset, p, K, p.Cout, 0);
+    return;
+  }
   dim3 grid((p.Cout + BM - 1) / BM, (K + BN - 1) / BN, 1);
   p.splits = pick_splits(static_cast<long long>(grid.x) * grid.y * p.S, (M + BK - 1) / BK);
   grid.z = p.S * p.splits;
   conv_wgrad_kernel<<<grid, THREADS, 0, at::cuda::getCurrentCUDAStream()>>>(
       x.data_ptr<float>(), dy.data_ptr<float>(), g_arena.data_ptr<float>() + g_offset, p);
   FLUTE_CUDA_CHECK(cudaGetLastError());
+}
+
+void slot_conv_set_impl(int64_t impl) {
+  TORCH_CHECK(impl >= 0 && impl <= 2, "impl: 0 = auto, 1 = FMA, 2 = tcgen05");
+  conv::g_conv_impl = static_cast<int>(impl);
 }
 
 }  // namespace flute

@@ -8,7 +8,26 @@ alive for layers whose input does not require grad (the stem convolution).
 """
 import torch
 
+import os
+
 from . import _ext
+
+_CONV_IMPLS = {"auto": 0, "fma": 1, "tcgen05": 2}
+_impl_applied = False
+
+
+def set_conv_impl(name: str) -> None:
+    """Select the slot-batched convolution kernels: ``tcgen05`` (kind::tf32 implicit GEMM, tensor cores), ``fma``
+    (exact fp32 CUDA-core tiles) or ``auto`` (tcgen05 whenever a slot's GEMM has >= 48 rows).  ``FLUTE_CONV_IMPL``
+    sets the initial choice."""
+    global _impl_applied
+    _ext.load().slot_conv_set_impl(_CONV_IMPLS[name])
+    _impl_applied = True
+
+
+def _ensure_impl():
+    if not _impl_applied:
+        set_conv_impl(os.environ.get("FLUTE_CONV_IMPL", "auto"))
 
 
 class SlotConv2d(torch.autograd.Function):
@@ -17,6 +36,7 @@ class SlotConv2d(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, dummy, W, G, w_off, Cout, KH, KW, stride, pad):
         ext = _ext.load()
+        _ensure_impl()
         x = x.contiguous()
         y = ext.slot_conv_fprop(x, W, w_off, Cout, KH, KW, stride, pad)
         _ext.count_launch(1)

@@ -2,8 +2,8 @@
 
 The reference ``torch.save``s ``latest_model.tar`` synchronously every round (``core/server.py:541-545``) — for
 ResNet-18 that is a 45 MB device→host copy plus a disk write on the critical path of every round.  Here the round
-only pays for a device-side snapshot (one flat D2D copy per tensor group on a side stream); a background thread
-moves the snapshot to pinned host memory and writes it.  If rounds complete faster than the disk, queued
+only pays for a device-side snapshot (ONE D2D copy per underlying storage — the whole parameter arena at once — on a
+side stream); a background thread moves the snapshot to pinned host memory (one D2H per storage) and writes it.  If rounds complete faster than the disk, queued
 snapshots for the same path are coalesced (latest wins) — the file on disk is always a complete, consistent
 checkpoint of some recent round, and ``flush()`` (called at shutdown, before any checkpoint is read back and by
 ``resume``) guarantees the final state is durable.
@@ -17,32 +17,97 @@ import threading
 import torch
 
 
-def _snapshot(obj, stream):
+def _walk(obj, fn):
     if torch.is_tensor(obj):
-        if obj.is_cuda:
-            with torch.cuda.stream(stream):
-                return obj.detach().clone()
-        return obj.detach().clone()
+        return fn(obj)
     if isinstance(obj, dict):
-        return {k: _snapshot(v, stream) for k, v in obj.items()}
+        return {k: _walk(v, fn) for k, v in obj.items()}
     if isinstance(obj, (list, tuple)):
-        return type(obj)(_snapshot(v, stream) for v in obj)
+        return type(obj)(_walk(v, fn) for v in obj)
     return obj
+
+
+def _storage_key(t):
+    return (t.device, t.untyped_storage().data_ptr())
+
+
+def _snapshot(obj, stream):
+    """Device-side copy of every tensor in ``obj``.  Tensors that are views into one big storage (the flat parameter
+    arena: every entry of ``model.state_dict()``) are snapshotted with ONE copy of that storage and rebuilt as views of
+    the copy — a round pays one D2D launch instead of one per parameter tensor."""
+    groups = {}
+
+    def collect(t):
+        if t.is_cuda:
+            g = groups.setdefault(_storage_key(t), [t.untyped_storage(), 0])
+            g[1] += t.numel() * t.element_size()
+        return t
+
+    _walk(obj, collect)
+    copies = {}
+    ctx = torch.cuda.stream(stream) if stream is not None else None
+    if ctx is not None:
+        ctx.__enter__()
+    try:
+        for key, (storage, used) in groups.items():
+            if used * 2 >= storage.nbytes():            # mostly covered: copy the storage once
+                whole = torch.empty(0, dtype=torch.uint8, device=key[0]).set_(storage)
+                copies[key] = whole.clone().untyped_storage()
+
+        def snap(t):
+            t = t.detach()
+            if t.is_cuda and _storage_key(t) in copies:
+                return torch.empty(0, dtype=t.dtype, device=t.device).set_(
+                    copies[_storage_key(t)], t.storage_offset(), t.size(), t.stride())
+            return t.clone()
+
+        return _walk(obj, snap)
+    finally:
+        if ctx is not None:
+            ctx.__exit__(None, None, None)
+
+
+_PINNED = {}
 
 
 def _to_host(obj):
-    if torch.is_tensor(obj):
-        return obj.cpu()
-    if isinstance(obj, dict):
-        return {k: _to_host(v) for k, v in obj.items()}
-    if isinstance(obj, (list, tuple)):
-        return type(obj)(_to_host(v) for v in obj)
-    return obj
+    """D2H of a snapshot: one pinned staging buffer per distinct device storage (reused by the single writer thread)."""
+    hosts = {}
+
+    def move(t):
+        if not t.is_cuda:
+            return t
+        key = _storage_key(t)
+        if key not in hosts:
+            storage = t.untyped_storage()
+            n = storage.nbytes()
+            buf = _PINNED.get(n)
+            if buf is None:
+                try:
+                    buf = torch.empty(n, dtype=torch.uint8).pin_memory()
+                except RuntimeError:
+                    buf = torch.empty(n, dtype=torch.uint8)
+                _PINNED[n] = buf
+            buf.copy_(torch.empty(0, dtype=torch.uint8, device=t.device).set_(storage), non_blocking=False)
+            hosts[key] = buf.untyped_storage()
+        return torch.empty(0, dtype=t.dtype).set_(hosts[key], t.storage_offset(), t.size(), t.stride())
+
+    return _walk(obj, move)
 
 
 class AsyncCheckpointer:
-    def __init__(self):
-        self._pending = {}                 # path -> (state, event)
+    """``min_interval``: seconds between two writes of the same path.  Rounds of the flagship take ~20 ms while pickling
+    + writing a 47 MB checkpoint takes longer; a writer that runs back to back competes with the training thread for
+    the GIL (every torch call re-acquires it).  Snapshots are still taken every round (latest wins); the file on disk
+    is at most ``min_interval`` (+ one write) stale, and ``flush()`` always writes the newest snapshot."""
+
+    def __init__(self, min_interval: float = 0.25):
+        self.min_interval = float(min_interval)
+        import sys
+        sys.setswitchinterval(min(sys.getswitchinterval(), 0.0005))   # bound GIL hand-over latency to the trainer
+        self._last_write = {}              # path -> time of the last completed write
+        self._flushing = 0
+        self._pending = {}                 # path -> (state | text, event)
         self._lock = threading.Lock()
         self._wake = threading.Condition(self._lock)
         self._busy = 0
@@ -68,23 +133,48 @@ class AsyncCheckpointer:
             self._pending[path] = (snap, ev)
             self._wake.notify()
 
+    def submit_text(self, path: str, text: str):
+        """Small text files (status_log.json, config.yaml): same latest-wins queue, written off the training thread."""
+        with self._wake:
+            if path in self._pending:
+                self.coalesced += 1
+            self._pending[path] = (text, None)
+            self._wake.notify()
+
+    def _due(self, now):
+        """First pending path whose rate limit has expired (all of them while flushing / stopping)."""
+        soonest = None
+        for path in self._pending:
+            wait = self._last_write.get(path, -1e30) + self.min_interval - now
+            if wait <= 0 or self._flushing or self._stop:
+                return path, 0.0
+            soonest = wait if soonest is None else min(soonest, wait)
+        return None, soonest
+
     def _loop(self):
+        import time
         while True:
             with self._wake:
-                while not self._pending and not self._stop:
-                    self._wake.wait()
-                if self._stop and not self._pending:
-                    return
-                path, (snap, ev) = next(iter(self._pending.items()))
-                del self._pending[path]
+                while True:
+                    if self._stop and not self._pending:
+                        return
+                    path, wait = self._due(time.monotonic())
+                    if path is not None:
+                        break
+                    self._wake.wait(timeout=wait)
+                snap, ev = self._pending.pop(path)
                 self._busy += 1
             try:
-                if ev is not None:
-                    ev.synchronize()
-                host = _to_host(snap)
                 tmp = path + ".tmp"
-                torch.save(host, tmp)
+                if isinstance(snap, str):
+                    with open(tmp, "w", encoding="utf8") as f:
+                        f.write(snap)
+                else:
+                    if ev is not None:
+                        ev.synchronize()
+                    torch.save(_to_host(snap), tmp)
                 os.replace(tmp, path)
+                self._last_write[path] = time.monotonic()
                 self.written += 1
             except Exception as e:  # never kill training because of a checkpoint
                 print("async checkpoint to {} failed: {}".format(path, e))
@@ -95,8 +185,13 @@ class AsyncCheckpointer:
 
     def flush(self):
         with self._wake:
-            while self._pending or self._busy:
-                self._wake.wait(timeout=0.05)
+            self._flushing += 1
+            self._wake.notify_all()
+            try:
+                while self._pending or self._busy:
+                    self._wake.wait(timeout=0.05)
+            finally:
+                self._flushing -= 1
 
     def close(self):
         self.flush()

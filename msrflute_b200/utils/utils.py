@@ -87,11 +87,20 @@ def print_cuda_stats():
 
 
 # ---------------------------------------------------------------------- IO
+_YAML_WRITTEN = {}
+
+
 def write_yaml(save_path, config):
+    """The reference rewrites ``config.yaml`` next to every checkpoint (every round); dumping it costs ~5 ms of host
+    time, so an unchanged config is not written again."""
     if hasattr(config, "to_dict"):
         config = config.to_dict()
+    key = repr(config)
+    if _YAML_WRITTEN.get(save_path) == key and os.path.exists(save_path):
+        return
     with open(save_path, "w", encoding="utf8") as f:
         yaml.safe_dump(config, f, default_flow_style=False)
+    _YAML_WRITTEN[save_path] = key
 
 
 def torch_save(save_path, state_or_model):
@@ -119,12 +128,31 @@ def try_except_save(save_fn, max_attempts=3, **kwargs):
     return False
 
 
-def update_json_log(log_path, status_info):
-    elems = {}
-    if os.path.exists(log_path):
+_JSON_LOGS = {}
+
+
+def update_json_log(log_path, status_info, background=False):
+    """Merge ``status_info`` into the JSON file at ``log_path`` (ref. ``utils.py:361-377``).  ``background=True``
+    hands the write to the async checkpoint thread (latest wins, durable after ``flush_checkpoints()``) — two file
+    operations per round otherwise sit on the round's critical path."""
+    elems = _JSON_LOGS.get(log_path) if background else None
+    if elems is None:
+        elems = {}
+        if os.path.exists(log_path):
+            with open(log_path, "r") as f:
+                elems = json.load(f)
+    elems.update(status_info)
+    if background:
+        from .async_ckpt import get_checkpointer
+        _JSON_LOGS[log_path] = elems
+        get_checkpointer().submit_text(log_path, json.dumps(elems))
+        return
+    if _JSON_LOGS.pop(log_path, None) is not None:      # a background write of this file may still be queued
+        from .async_ckpt import flush_checkpoints
+        flush_checkpoints()
         with open(log_path, "r") as f:
             elems = json.load(f)
-    elems.update(status_info)
+        elems.update(status_info)
     tmp = log_path + ".tmp"
     with open(tmp, "w") as f:
         json.dump(elems, f)

@@ -159,10 +159,25 @@ def test_group_norm_fwd_bwd(shape, cpg, per_group, dtype, fuse):
         assert torch.allclose(a, e, **tol), (a - e).abs().max()
 
 
-def test_engine_round_matches_generic_path():
-    """One FedAvg round through the device engine (graphs, slots, fused accumulate) == the generic per-client path."""
+@pytest.mark.parametrize("conv_impl", ["fma", "auto"])
+def test_engine_round_matches_generic_path(conv_impl):
+    """One FedAvg round through the device engine (graphs, slots, fused accumulate) == the generic per-client path.
+    ``fma``: exact-fp32 convolutions, tight tolerance.  ``auto``: tcgen05 tf32 convolutions (cuDNN's default precision
+    too); GroupNorm over 2-channel groups on 1x1 feature maps is a sign function of a difference, so 1e-3 operand
+    rounding is amplified ~1e4x in this configuration — only a sanity bound is asserted here, the tf32 kernels are
+    checked against fp32 with tight bounds in ``test_slot_conv_matches_conv2d`` and on a well-conditioned ResNet in
+    ``test_slot_batched_resnet_matches_per_client_models[auto]``."""
     import bench
     from msrflute_b200.core import client as client_mod
+    from msrflute_b200.ops import slot_ops
+    slot_ops.set_conv_impl(conv_impl)
+    try:
+        _engine_round_check(bench, 0.02 if conv_impl == "fma" else 0.5)
+    finally:
+        slot_ops.set_conv_impl("auto")
+
+
+def _engine_round_check(bench, tol):
     torch.manual_seed(0)
     torch.backends.cudnn.allow_tf32 = False          # the generic path uses cuDNN: compare fp32 with fp32
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -187,11 +202,11 @@ def test_engine_round_matches_generic_path():
     assert [o["ns"] for o in outs_e] == [o["ns"] for o in outs_g] == [100, 100, 100]
     assert [o["pl"]["weight"] for o in outs_e] == [100.0] * 3
     ne, ng = acc_e.norm().item(), acc_g.norm().item()
-    assert abs(ne / ng - 1.0) < 0.02, (ne, ng)
+    assert abs(ne / ng - 1.0) < tol, (ne, ng)
     cos = torch.dot(acc_e, acc_g) / (acc_e.norm() * acc_g.norm())
-    assert cos > 0.98, cos
+    assert cos > 1.0 - tol, cos
     for a, b in zip(outs_e, outs_g):
-        assert abs(a["tl"] / b["tl"] - 1.0) < 1e-2 and abs(float(a["rg"]) / float(b["rg"]) - 1.0) < 1e-2
+        assert abs(a["tl"] / b["tl"] - 1.0) < tol / 2 and abs(float(a["rg"]) / float(b["rg"]) - 1.0) < tol / 2
     for o in outs_e:
         assert o["tl"] > 0 and math.isfinite(o["tl"]) and o["rg"] > 0
     srv.end_training()
@@ -236,11 +251,23 @@ def test_gemm_tcgen05_matches_fp32_reference(G, M, N, K, epi):
 
 @pytest.mark.parametrize("cfg", [  # (S, B, Cin, H, Cout, k, stride, pad)
     (3, 20, 3, 32, 64, 7, 2, 3), (2, 20, 64, 8, 64, 3, 1, 1), (4, 20, 64, 8, 128, 3, 2, 1), (2, 20, 64, 8, 128, 1, 2, 0),
-    (3, 20, 256, 2, 512, 3, 2, 1), (2, 20, 512, 1, 512, 3, 1, 1), (1, 5, 7, 9, 11, 3, 1, 1)])
-def test_slot_conv_matches_conv2d(cfg):
+    (3, 20, 256, 2, 512, 3, 2, 1), (2, 20, 512, 1, 512, 3, 1, 1), (1, 5, 7, 9, 11, 3, 1, 1),
+    (2, 20, 128, 4, 128, 3, 1, 1), (2, 20, 256, 2, 256, 3, 1, 1), (2, 7, 5, 13, 70, 5, 2, 2)])
+@pytest.mark.parametrize("impl", ["fma", "tcgen05"])
+def test_slot_conv_matches_conv2d(cfg, impl):
+    """Both implementations of the slot-batched convolution (fp32 FMA tiles; tcgen05 kind::tf32 implicit GEMM with
+    producer-warp im2col) against per-slot ``F.conv2d`` in fp32."""
     ext = _ext()
     if not hasattr(ext, "slot_conv_fprop"):
         pytest.skip("slot conv not built")
+    ext.slot_conv_set_impl(1 if impl == "fma" else 2)
+    try:
+        _check_slot_conv(cfg, tf32=impl == "tcgen05")
+    finally:
+        ext.slot_conv_set_impl(0)
+
+
+def _check_slot_conv(cfg, tf32):
     from msrflute_b200.ops.slot_ops import SlotConv2d
     S, B, Cin, H, Cout, k, stride, pad = cfg
     torch.manual_seed(5)
@@ -261,17 +288,35 @@ def test_slot_conv_matches_conv2d(cfg):
         xs = x[s].detach().clone().requires_grad_(True)
         ys = torch.nn.functional.conv2d(xs, w, None, stride, pad)
         ys.backward(dy[s])
+        gw = G[s, off:off + n].view_as(w)
+        if tf32:        # 10-bit mantissa operands, fp32 accumulation: bound the error by the size of the result
+            for got, ref in ((y[s], ys), (x.grad[s], xs.grad), (gw, w.grad)):
+                err = (got - ref).abs().max().item()
+                assert err <= 4e-3 * ref.abs().max().item() + 1e-5, (err, ref.abs().max().item())
+            continue
         assert torch.allclose(y[s], ys, atol=2e-3, rtol=1e-3), (y[s] - ys).abs().max()
         assert torch.allclose(x.grad[s], xs.grad, atol=2e-3, rtol=1e-3), (x.grad[s] - xs.grad).abs().max()
-        gw = G[s, off:off + n].view_as(w)
         assert torch.allclose(gw, w.grad, atol=5e-3, rtol=2e-3), (gw - w.grad).abs().max()
     assert G[:, :off].abs().sum() == 0 and G[:, off + n:].abs().sum() == 0         # nothing written outside the tensor
 
 
-def test_slot_batched_resnet_matches_per_client_models():
+@pytest.mark.parametrize("conv_impl", ["fma", "auto"])
+def test_slot_batched_resnet_matches_per_client_models(conv_impl):
     ext = _ext()
     if not hasattr(ext, "slot_conv_fprop"):
         pytest.skip("slot conv not built")
+    from msrflute_b200.ops import slot_ops
+    slot_ops.set_conv_impl(conv_impl)
+    try:
+        if conv_impl == "fma":      # the flagship configuration (2 channels per group, 32x32 inputs), exact fp32 convs
+            _slot_resnet_check(loss_tol=2e-3, grad_tol=1.5e-2, cpg=2, hw=32)
+        else:                       # tf32 convs: a configuration where GroupNorm does not amplify rounding chaotically
+            _slot_resnet_check(loss_tol=1e-2, grad_tol=5e-2, cpg=16, hw=64)
+    finally:
+        slot_ops.set_conv_impl("auto")
+
+
+def _slot_resnet_check(loss_tol, grad_tol, cpg, hw):
     import copy
     from msrflute_b200.models.resnet_gn import RESNET
     from msrflute_b200.models.slot_resnet import SlotBatchedResNet
@@ -280,7 +325,7 @@ def test_slot_batched_resnet_matches_per_client_models():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     S, B = 3, 20
-    base = RESNET({"group_norm": 2, "num_classes": 100}).cuda()
+    base = RESNET({"group_norm": cpg, "num_classes": 100}).cuda()
     assert SlotBatchedResNet.supports(base)
     lay = ArenaLayout.from_module(base)
     W = torch.zeros(S, lay.padded_numel, device="cuda")
@@ -294,7 +339,7 @@ def test_slot_batched_resnet_matches_per_client_models():
         adopt_module(m, with_grad=True, param_buffer=W[s], grad_buffer=torch.zeros(lay.padded_numel, device="cuda"))
         models.append(m)
     slot = SlotBatchedResNet(models[0], lay, W, G)
-    x = torch.randn(S, B, 3, 32, 32, device="cuda") * 50 + 100
+    x = torch.randn(S, B, 3, hw, hw, device="cuda") * 50 + 100
     y = torch.randint(0, 100, (S, B), device="cuda")
     losses = slot.losses(x, y)
     losses.sum().backward()
@@ -303,11 +348,11 @@ def test_slot_batched_resnet_matches_per_client_models():
         m.zero_grad()
         l = m.loss({"x": x[s], "y": y[s]})
         l.backward()
-        assert abs(l.item() - losses[s].item()) < 2e-3 * max(1.0, abs(l.item())), (l.item(), losses[s].item())
+        assert abs(l.item() - losses[s].item()) < loss_tol * max(1.0, abs(l.item())), (l.item(), losses[s].item())
         ref = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
         got = torch.cat([v.reshape(-1) for v in lay.views(G[s])])
         rel = (ref - got).norm() / ref.norm()
-        assert rel < 1.5e-2, rel       # fp32 atomics + GroupNorm over 2-element groups amplify rounding
+        assert rel < grad_tol, rel     # fp32 atomics + GroupNorm over 2-element groups amplify rounding
 
 
 def test_tc_linear_forward_backward_matches_fp32():

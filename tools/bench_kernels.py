@@ -95,15 +95,22 @@ def bench_conv(out):
         x = torch.randn(S, B, Cin, H, H, device="cuda")
         y = ext.slot_conv_fprop(x, W, 0, Cout, k, k, stride, pad)
         dy = torch.randn_like(y)
+        ext.slot_conv_set_impl(1)
         f, _ = timeit(lambda: ext.slot_conv_fprop(x, W, 0, Cout, k, k, stride, pad))
         d, _ = timeit(lambda: ext.slot_conv_dgrad(dy, W, 0, Cin, H, H, k, k, stride, pad))
         wg, _ = timeit(lambda: ext.slot_conv_wgrad(x, dy, G, 0, k, k, stride, pad))
+        ext.slot_conv_set_impl(2)
+        tf, _ = timeit(lambda: ext.slot_conv_fprop(x, W, 0, Cout, k, k, stride, pad))
+        td, _ = timeit(lambda: ext.slot_conv_dgrad(dy, W, 0, Cin, H, H, k, k, stride, pad))
+        tw, _ = timeit(lambda: ext.slot_conv_wgrad(x, dy, G, 0, k, k, stride, pad))
+        ext.slot_conv_set_impl(0)
         fl = 2.0 * S * B * y.shape[3] * y.shape[4] * Cout * Cin * k * k
         torch.backends.cudnn.allow_tf32 = True
         xs, ws = x[0], W[0, :n].view(Cout, Cin, k, k)
         lib, _ = timeit(lambda: [torch.nn.functional.conv2d(x[s], W[s, :n].view(Cout, Cin, k, k), None, stride, pad) for s in range(S)])
-        rows.append({"layer": name, "fprop_ms": f, "dgrad_ms": d, "wgrad_ms": wg, "dense_gflop": fl / 1e9,
-                     "fprop_dense_tflops": fl / f / 1e9, "cudnn_10_launches_fprop_ms": lib})
+        rows.append({"layer": name, "fma_fprop_ms": f, "fma_dgrad_ms": d, "fma_wgrad_ms": wg,
+                     "tcgen05_fprop_ms": tf, "tcgen05_dgrad_ms": td, "tcgen05_wgrad_ms": tw, "dense_gflop": fl / 1e9,
+                     "fma_fprop_dense_tflops": fl / f / 1e9, "tcgen05_fprop_dense_tflops": fl / tf / 1e9, "cudnn_10_launches_fprop_ms": lib})
         print(rows[-1])
     out["slot_conv"] = rows
 
