@@ -415,8 +415,12 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
   }
   if (warp == 8) tmem_alloc(tmem_ptr, TN);
   if (tid >= TM && tid < TM + p.ntaps) {
+    // .x = the tap's separable address offset: fprop  x[.., oh*s-pad+kh, ow*s-pad+kw]      -> + kh*Wi + kw
+    //                                          dgrad dy[.., (ih+pad-kh)/s, (iw+pad-kw)/s]   -> - (kh/s)*Wo - kw/s
+    //      (when s divides ih+pad-kh the quotient is floor((ih+pad)/s) - floor(kh/s));  .y = kh << 16 | kw
     const int t = p.taps[tid - TM], kh = t >> 8, kw = t & 255;
-    tap_table[tid - TM] = make_int2(kh * (MODE == DGRAD ? p.Wo : p.Wi) + kw, (kh << 16) | kw);
+    const int off = MODE == DGRAD ? -((kh / p.stride) * p.Wo + kw / p.stride) : kh * p.Wi + kw;
+    tap_table[tid - TM] = make_int2(off, (kh << 16) | kw);
   }
   if (MODE == WGRAD && tid < TM) {                   // per-row (ci, tap) decode of this tile, shared by all stages
     const int k = r_tile0 + tid;
@@ -440,21 +444,35 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
   if (tid < T_PRODUCERS) {
     // ------------------------------------------------------------------------------------------ producers
     const int row = tid & (TM - 1), khalf = tid >> 7;
-    // row-gather state (fprop / dgrad): this thread's output pixel
-    bool rvalid = false;
-    int base = 0, h0 = 0, w0 = 0;
-    const int sshift = p.stride == 1 ? 0 : p.stride == 2 ? 1 : p.stride == 4 ? 2 : -1;
-    if (MODE == FPROP) {
+    // row-gather state (fprop / dgrad): this thread's pixel.  Which taps fall inside the image is a property of the
+    // pixel alone, so it is decided once (one bit per tap) and the per-element work in the stage loop is: test a bit,
+    // add the tap's table offset, load, select.
+    unsigned long long tap_ok = 0ull;
+    int base = 0;                                      // offset of (b, channel 0, pixel-dependent part)
+    if (MODE == FPROP || MODE == DGRAD) {
       const int m = r_tile0 + row;
       if (m < R) {
-        const int b = m / HoWo, r = m - b * HoWo, oh = r / p.Wo, ow = r - oh * p.Wo;
-        rvalid = true; base = b * p.Cin * HiWi; h0 = oh * p.stride - p.pad; w0 = ow * p.stride - p.pad;
-      }
-    } else if (MODE == DGRAD) {
-      const int m = r_tile0 + row;
-      if (m < R) {
-        const int b = m / HiWi, r = m - b * HiWi, ih = r / p.Wi, iw = r - ih * p.Wi;
-        rvalid = true; base = b * p.Cout * HoWo; h0 = ih + p.pad; w0 = iw + p.pad;
+        const int HW = MODE == FPROP ? HoWo : HiWi, Wd = MODE == FPROP ? p.Wo : p.Wi;
+        const int b = m / HW, r = m - b * HW, ph = r / Wd, pw = r - ph * Wd;
+        if (MODE == FPROP) {
+          const int h0 = ph * p.stride - p.pad, w0 = pw * p.stride - p.pad;
+          base = b * p.Cin * HiWi + h0 * p.Wi + w0;
+          for (int t = 0; t < p.ntaps; ++t) {
+            const int2 tp = tap_table[t];
+            const int ih = h0 + (tp.y >> 16), iw = w0 + (tp.y & 0xFFFF);
+            if (static_cast<unsigned>(ih) < static_cast<unsigned>(p.Hi) && static_cast<unsigned>(iw) < static_cast<unsigned>(p.Wi))
+              tap_ok |= 1ull << t;
+          }
+        } else {
+          const int h0 = ph + p.pad, w0 = pw + p.pad;
+          base = b * p.Cout * HoWo + (h0 / p.stride) * p.Wo + w0 / p.stride;
+          for (int t = 0; t < p.ntaps; ++t) {
+            const int2 tp = tap_table[t];
+            const int th = h0 - (tp.y >> 16), tw = w0 - (tp.y & 0xFFFF);          // = oh * stride, ow * stride
+            if (th >= 0 && tw >= 0 && th % p.stride == 0 && tw % p.stride == 0 && th / p.stride < p.Ho && tw / p.stride < p.Wo)
+              tap_ok |= 1ull << t;
+          }
+        }
       }
     }
     for (int it = 0; it < nst; ++it) {
@@ -464,41 +482,23 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
       uint8_t* sb = sa + T_A_BYTES;
       const int r0 = (st_begin + it) * TK;
       if (MODE == FPROP || MODE == DGRAD) {
-        // ---- A: row gather, 16 reduction indices of this thread's pixel.  Branch-free: out-of-range elements load
-        // element 0 and are zeroed by a select, so all 16 loads are in flight together.
+        // ---- A: row gather, 16 reduction indices (channel, tap) of this thread's pixel.  Branch-free: masked
+        // elements load element 0 and are zeroed by a select, so all 16 loads are in flight together.
         const int k = r0 + khalf * 16;
         const int c0 = k / p.ntaps;                         // ci (fprop) / co (dgrad) of the first index
+        const int CS = MODE == FPROP ? HiWi : HoWo;         // channel stride of the gathered tensor
         int ti = k - c0 * p.ntaps;
-        int cbase = base + c0 * (MODE == FPROP ? HiWi : HoWo);
+        int cbase = base + c0 * CS;
+        const int nvalid = RED - k;                         // reduction indices left (only the last stage is partial)
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int2 tp = tap_table[ti];
-          const int kh = tp.y >> 16, kw = tp.y & 0xFFFF;
-          bool ok = rvalid && (k + j < RED);
-          int idx;
-          if (MODE == FPROP) {
-            const int ih = h0 + kh, iw = w0 + kw;
-            ok = ok && static_cast<unsigned>(ih) < static_cast<unsigned>(p.Hi) && static_cast<unsigned>(iw) < static_cast<unsigned>(p.Wi);
-            idx = cbase + ih * p.Wi + iw;
-          } else {
-            const int th = h0 - kh, tw = w0 - kw;           // = oh * stride, ow * stride
-            int oh, ow;
-            if (sshift >= 0) {
-              ok = ok && (((th | tw) & (p.stride - 1)) == 0);
-              oh = th >> sshift; ow = tw >> sshift;         // negative th/tw stay negative -> fail the unsigned compare
-            } else {
-              oh = th / p.stride; ow = tw / p.stride;
-              ok = ok && th >= 0 && tw >= 0 && oh * p.stride == th && ow * p.stride == tw;
-            }
-            ok = ok && static_cast<unsigned>(oh) < static_cast<unsigned>(p.Ho) && static_cast<unsigned>(ow) < static_cast<unsigned>(p.Wo);
-            idx = cbase + oh * p.Wo + ow;
-          }
-          const float xv = __ldg(a_src + (ok ? idx : 0));
+          const bool ok = ((tap_ok >> ti) & 1ull) != 0ull && j < nvalid;
+          const float xv = __ldg(a_src + (ok ? cbase + tap_table[ti].x : 0));
           v[j] = ok ? xv : 0.f;
           const bool wrap = ++ti == p.ntaps;
           ti = wrap ? 0 : ti;
-          cbase += wrap ? (MODE == FPROP ? HiWi : HoWo) : 0;
+          cbase += wrap ? CS : 0;
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
