@@ -177,7 +177,7 @@ class Server:
         flat_ok = torch.is_tensor(weights)
         ctrl = {"cmd": command, "lr": lr, "round": nround, "assign": assign, "mode": mode, "fused": fused,
                 "sync": ("flat" if flat_ok else "list" if weights is not None else "none") if sync_weights else "none",
-                "extra": extra or {}}
+                "extra": extra or {}, "defer": bool(defer and fused and command == COMMAND_TRAIN)}
         if comm.size > 1:
             comm.bcast_object(ctrl, src=0)
             Server._sync_weights(comm, worker, weights, ctrl["sync"])
@@ -190,12 +190,17 @@ class Server:
             mine = assign[comm.rank if comm.size > 1 else 0]
             if command == COMMAND_TRAIN:
                 local_out = worker.train_clients(mine, (lr, None, nround), fused=fused, extra=ctrl["extra"],
-                                                 defer=defer and comm.size == 1)
-                if not isinstance(local_out, list):          # DeferredRound
+                                                 defer=ctrl["defer"])
+                if comm.size == 1 and not isinstance(local_out, list):      # DeferredRound
                     yield local_out
                     return
             else:
                 local_out = worker.eval_clients(mine, mode, (lr, None, nround))
+        if ctrl["defer"] and comm.size > 1:
+            # multi-rank deferred round: the cross-rank reduction of the accumulators and of Σ weight is enqueued
+            # right behind the local training; per-client records are gathered (host, gloo) only on resolve()
+            yield _finish_deferred(comm, worker, local_out, len(clients))
+            return
         for o in local_out:
             yield o
 
@@ -247,10 +252,54 @@ class Server:
         return Server.dispatch_clients(clients, server_data, COMMAND_TESTVAL, mode, single_worker=single_worker, **kw)
 
     @staticmethod
+    def sync_nodes(options=None):
+        """Barrier across all ranks driven from the server (workers sit in their command loop).  Every rank drains its
+        GPU first, so "barrier + synchronize" brackets of a benchmark really bracket device work.  ``options`` is
+        applied on every worker before the barrier (e.g. ``{"resident": False}`` switches the engines to streaming)."""
+        comm = get_comm()
+        if comm.size > 1 and comm.rank == 0:
+            comm.bcast_object({"cmd": COMMAND_SYNC_NODES, "sync": "none", "assign": {}, "options": options or {}}, src=0)
+        worker = _Runtime.worker
+        if worker is not None and options:
+            worker.apply_options(options)
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        if comm.size > 1:
+            comm.barrier()
+
+    @staticmethod
     def terminate_workers(terminate=True):
         comm = get_comm()
         if terminate and comm.size > 1 and comm.rank == 0:
             comm.bcast_object({"cmd": COMMAND_TERMINATE}, src=0)
+
+
+def _finish_deferred(comm, worker, local, n_clients):
+    """Every rank calls this with its (possibly deferred / empty) local result, in the same order: NCCL/symm reduce of
+    the accumulators → all-reduce of Σ weight → (on resolve) host sync + gloo gather of the per-client records."""
+    from .engine import DeferredRound
+    acc = worker.accumulator()
+    if isinstance(local, DeferredRound):
+        wsum = local.weight_sum.reshape(1).float().clone()
+    else:
+        wsum = torch.tensor([float(sum((o.get("pl") or {}).get("weight", 0.0) for o in local))], device=acc.device)
+    # Σ weight first: with the symmetric-memory transport the server's stream is [barrier A, update kernel, barrier B]
+    # and the update kernel needs the total, so the (NCCL) all-reduce must precede barrier A on every rank.
+    comm.all_reduce_(wsum)
+    comm.reduce_accumulators(acc, dst=0)
+    if comm.rank != 0 and comm.kind != "symm":
+        acc.zero_()
+
+    def resolve():
+        outs = local.resolve() if isinstance(local, DeferredRound) else list(local)
+        records = comm.gather_objects([_strip(o) for o in outs])
+        merged = list(outs)
+        for r, recs in enumerate(records):
+            if r != comm.rank:
+                merged.extend(recs)
+        return merged
+
+    return DeferredRound(n_clients, wsum[0], resolve)
 
 
 def _strip(o):
@@ -280,6 +329,7 @@ class Worker:
         self._weights_list = None
         self.engine = None       # optional device-resident multi-client engine (core/engine.py)
         self.round_events = []   # CUDA events recorded after every TRAIN command (device-side round timing)
+        self.sync_events = []    # CUDA events recorded at every server-driven sync_nodes()
 
     # ---- weight / accumulator buffers -------------------------------------
     def _arena(self):
@@ -387,6 +437,15 @@ class Worker:
             if cmd == COMMAND_UPDATE:
                 Server._sync_weights(comm, self, self.weight_buffer(), ctrl.get("sync", "flat"))
                 continue
+            if cmd == COMMAND_SYNC_NODES:
+                self.apply_options(ctrl.get("options") or {})
+                if torch.cuda.is_available():
+                    torch.cuda.synchronize()
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record()
+                    self.sync_events.append(ev)
+                comm.barrier()
+                continue
             if ctrl["sync"] == "flat":
                 comm.broadcast_weights(self.weight_buffer(), src=0)
                 self.weights_updated()
@@ -394,6 +453,16 @@ class Worker:
                 self.set_weights(comm.bcast_object(None, src=0))
             mine = ctrl["assign"].get(comm.rank, [])
             if cmd == COMMAND_TRAIN:
+                if ctrl.get("defer"):
+                    res = self.train_clients(mine, (ctrl["lr"], None, ctrl["round"]), fused=True,
+                                             extra=ctrl.get("extra"), defer=True) if mine else []
+                    _finish_deferred(comm, self, res, len(mine)).resolve()
+                    if torch.cuda.is_available():
+                        ev = torch.cuda.Event(enable_timing=True)
+                        ev.record()
+                        self.round_events.append(ev)
+                        del self.round_events[:-64]
+                    continue
                 outs = self.train_clients(mine, (ctrl["lr"], None, ctrl["round"]), fused=ctrl["fused"],
                                           extra=ctrl.get("extra"))
                 comm.gather_objects([_strip(o) for o in outs])
@@ -407,20 +476,23 @@ class Worker:
                     ev = torch.cuda.Event(enable_timing=True)
                     ev.record()
                     self.round_events.append(ev)
+                    del self.round_events[:-64]
             elif cmd == COMMAND_TESTVAL:
                 comm.gather_objects(self.eval_clients(mine, ctrl["mode"], (0.0, None, 0)))
-            elif cmd == COMMAND_SYNC_NODES:
-                comm.barrier()
             else:
                 raise AssertionError("unknown command {}".format(cmd))
 
-    def timed_region_ms(self, warmup, steps):
-        """Device time this rank spent between the end of round ``warmup`` and the end of round ``warmup+steps``."""
-        ev = self.round_events
-        if len(ev) < warmup + steps or warmup < 1:
+    def apply_options(self, options):
+        if "resident" in options and self.engine is not None:
+            self.engine.set_resident(bool(options["resident"]))
+
+    def sync_region_ms(self, first, second):
+        """Device time between this rank's ``first``-th and ``second``-th ``sync_nodes`` (CUDA events)."""
+        ev = self.sync_events
+        if len(ev) <= max(first, second):
             return 0.0
-        ev[warmup + steps - 1].synchronize()
-        return float(ev[warmup - 1].elapsed_time(ev[warmup + steps - 1]))
+        ev[second].synchronize()
+        return float(ev[first].elapsed_time(ev[second]))
 
     # ---- reference single-process entry points ------------------------------------------
     def trigger_train(self, lr, model_params, nround, client_idx):

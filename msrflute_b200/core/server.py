@@ -445,9 +445,10 @@ class OptimizationServer(federated.Server):
     def _can_defer(self, apply_privacy_metrics):
         """Deferred read-back needs a round whose server side never looks at per-client host values."""
         dp = self.config.get("dp_config", None) or {}
-        return (torch.cuda.is_available() and not apply_privacy_metrics and not self.do_profiling
+        force = os.environ.get("FLUTE_FORCE_DEFER") == "1"        # CPU tests of the multi-rank deferred protocol
+        return ((torch.cuda.is_available() or force) and not apply_privacy_metrics and not self.do_profiling
                 and not dp.get("enable_global_dp", False) and not self.config.get("dump_norm_stats", False)
-                and not self.strategy.skip_model_update and federated.get_comm().size == 1)
+                and not self.strategy.skip_model_update)
 
     def _fused_server_update(self, weights, curr_iter, num_clients_curr_iter, log_metric, wsum=None):
         """Fast path: the weighted pseudo-gradient sums (already reduced onto this rank, or peer-mapped when the

@@ -41,6 +41,7 @@ class SymmComm(CollectiveComm):
         except Exception:
             pass
         self._bufs = {}          # name -> (local tensor, handle)
+        self._peer_cache = {}    # name -> [tensor of rank 0, rank 1, ...] (peer views are created once)
         self._ext = _ext.load(required=True)
         # probe: fail early (→ collective fallback) if peer mapping is not possible on this box
         probe = self._alloc("probe", 1024, torch.float32)
@@ -66,10 +67,14 @@ class SymmComm(CollectiveComm):
         return self._alloc(name, numel, dtype)[0]
 
     def _peers(self, name) -> List[torch.Tensor]:
+        cached = self._peer_cache.get(name)
+        if cached is not None:
+            return cached
         t, hdl = self._bufs[name]
         out = []
         for r in range(self.size):
             out.append(t if r == self.rank else hdl.get_buffer(r, (t.numel(),), t.dtype))
+        self._peer_cache[name] = out
         return out
 
     def _handle_of(self, t):

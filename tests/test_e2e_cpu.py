@@ -41,7 +41,7 @@ def _config(tmp, rounds=3, resume=False, strategy="FedAvg", extra_server=None, e
     return path
 
 
-def _run(tmp, cfg_path, nproc=1, port=29611, timeout=900):
+def _run(tmp, cfg_path, nproc=1, port=29611, timeout=900, extra_env=None):
     out = os.path.join(tmp, "out")
     cmd = [sys.executable]
     if nproc > 1:
@@ -50,6 +50,7 @@ def _run(tmp, cfg_path, nproc=1, port=29611, timeout=900):
     cmd += [os.path.join(ROOT, "e2e_trainer.py"), "-config", cfg_path, "-outputPath", out, "-dataPath", tmp,
             "-task", "cv_lr_mnist", "-backend", "gloo", "-experiment", "exp"]
     env = dict(os.environ, PYTHONPATH=ROOT, FLUTE_ALLOW_FALLBACK="1", CUDA_VISIBLE_DEVICES="")
+    env.update(extra_env or {})
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return os.path.join(out, "exp"), r.stdout + r.stderr
@@ -128,3 +129,16 @@ def test_two_ranks_gloo_every_rank_trains_and_server_aggregates(tmp_path):
     m = _metrics(exp)
     assert m["Val loss"][-1] < m["Val loss"][0]
     assert "Worker on node 1: process started" in log
+
+
+def test_two_ranks_gloo_deferred_round_protocol(tmp_path):
+    """The deferred multi-rank round (reduce Σw → reduce accumulators → records gathered at the end of the round) is
+    what runs on multi-GPU jobs; ``FLUTE_FORCE_DEFER`` exercises the same control flow on CPU/gloo."""
+    tmp = str(tmp_path)
+    _write_data(tmp)
+    exp, log = _run(tmp, _config(tmp, rounds=3), nproc=2, port=29617, extra_env={"FLUTE_FORCE_DEFER": "1"})
+    st = json.load(open(os.path.join(exp, "models", "status_log.json")))
+    assert st["i"] == 3
+    m = _metrics(exp)
+    assert m["Val loss"][-1] < m["Val loss"][0]
+    assert len(m["Training loss"]) == 3
