@@ -18,7 +18,9 @@ class Dataset(BaseDataset):
         self.labels = np.concatenate([np.asarray(self.user_data_label[u]) for u in users]) if users else np.zeros((0,))
 
     def __getitem__(self, idx):
-        return self.features[idx].astype(np.float32).T, self.labels[idx]
+        # Samples are stored (H, W, C); the model transposes (N, H, W, C) -> (N, C, W, H) itself.  (The reference stores
+        # torchvision CHW tensors and returns ``.T`` = (W, H, C) here, ``dataset.py:21`` — same layout downstream.)
+        return self.features[idx].astype(np.float32), self.labels[idx]
 
     def __len__(self):
         return len(self.features)

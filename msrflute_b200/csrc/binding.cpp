@@ -47,6 +47,11 @@ at::Tensor slot_conv_dgrad(at::Tensor dy, at::Tensor w_arena, int64_t w_offset, 
 void slot_conv_wgrad(at::Tensor x, at::Tensor dy, at::Tensor g_arena, int64_t g_offset, int64_t KH, int64_t KW,
                      int64_t stride, int64_t pad);
 void slot_conv_set_impl(int64_t impl);
+at::Tensor seg_minmax(at::Tensor flat, at::Tensor seg);
+std::vector<at::Tensor> quantize_segments(at::Tensor flat, at::Tensor seg, at::Tensor stats, int64_t bits, bool emit_codes);
+at::Tensor local_dp(at::Tensor flat, double max_grad, double sigma, bool clip_only, int64_t seed);
+std::vector<at::Tensor> softmax_ce(at::Tensor logits, at::Tensor target, double grad_scale, int64_t ignore_index, bool want_grad);
+at::Tensor cosine_stats(at::Tensor a, at::Tensor b);
 }  // namespace flute
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -69,6 +74,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("slot_conv_dgrad", &flute::slot_conv_dgrad);
   m.def("slot_conv_wgrad", &flute::slot_conv_wgrad);
   m.def("slot_conv_set_impl", &flute::slot_conv_set_impl);
+  m.def("seg_minmax", &flute::seg_minmax);
+  m.def("quantize_segments", &flute::quantize_segments);
+  m.def("local_dp", &flute::local_dp);
+  m.def("softmax_ce", &flute::softmax_ce);
+  m.def("cosine_stats", &flute::cosine_stats);
   m.def("gru_cell_fwd", &flute::gru_cell_fwd);
   m.def("gru_cell_bwd", &flute::gru_cell_bwd);
   m.def("lstm_cell_fwd", &flute::lstm_cell_fwd);

@@ -19,6 +19,7 @@ import numpy as np
 import torch as T
 from scipy.special import betainc, betaln
 
+from ...ops import misc_ops
 from ...utils import print_rank
 from . import analysis as privacy_analysis
 from .analysis import RDPIncrementalAccountant
@@ -160,7 +161,11 @@ def apply_local_dp(trainer, weight, dp_config, add_weight_noise):
     flat, writer = _flat_grad(trainer.model)
     grad_norm = flat.norm()
     max_grad = dp_config["max_grad"]
+    fused = writer is None and flat.is_cuda and flat.is_contiguous() and flat.dtype == T.float32
     if dp_config["eps"] < 0:
+        if fused:                                            # clip only: one reduction + one scale kernel
+            misc_ops.local_dp_(flat, max_grad, 0.0, True)
+            return weight
         coef = T.clamp(max_grad / grad_norm, max=1.0)        # clip only, stays on device
         out = flat.mul_(coef) if writer is None else flat * coef
         if writer is not None:
@@ -173,7 +178,9 @@ def apply_local_dp(trainer, weight, dp_config, add_weight_noise):
     sens = np.sqrt(max_grad ** 2 + (dp_config["max_weight"] ** 2 if add_weight_noise else 0.0))
     sigma = compute_LDP_noise_std(eps, sens, delta)
     scale = max_grad / grad_norm
-    if writer is None:
+    if fused:                                                # scale to C and add Philox Gaussian noise in one pass
+        misc_ops.local_dp_(flat, max_grad, float(sigma), False, seed=int(T.randint(0, 2 ** 62, (1,)).item()))
+    elif writer is None:
         flat.mul_(scale).add_(T.randn_like(flat), alpha=float(sigma))
     else:
         writer(flat * scale + float(sigma) * T.randn_like(flat))

@@ -7,9 +7,9 @@ values with ``|g| <= thresh`` are zeroed.  The reference keeps the result in fp3
 
 Here the same transform is closed-form (``level = clamp(ceil((g−lo)/w − 1/2), 0, L−1)``; no ``linspace`` /
 ``bucketize`` tables) and runs over the flat gradient arena with a per-tensor segment table; on CUDA it is
-two hand-written kernels (``csrc/quant_kernels.cu``: segmented min/max + radix-select quantile, then
-encode) that can ALSO emit the packed ``quant_bits``-wide codes + sparsity bitmap — real wire compression
-for the gather path — with ``dequantize_packed`` as the inverse fused into the server reduce.
+two hand-written kernels (``csrc/misc_kernels.cu``: segmented min/max, then one encode kernel for the whole
+arena) that can ALSO emit the ``quant_bits``-wide level codes + keep mask — the wire format of
+``ops.quant_ops.pack_segments`` / ``unpack_add_``.
 """
 import logging
 from typing import Optional, Tuple

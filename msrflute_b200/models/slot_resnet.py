@@ -10,6 +10,7 @@ group counts) — the numbers come from the arenas.
 import torch
 import torch.nn.functional as F
 
+from ..ops import misc_ops
 from ..ops.slot_ops import SlotConv2d, SlotGroupNorm, SlotLinear
 from .resnet_gn import BasicBlock, Bottleneck, GroupNorm2d, RESNET
 
@@ -77,5 +78,5 @@ class SlotBatchedResNet:
         """Per-slot mean cross-entropy [S] (the sum of which is back-propagated)."""
         logits = self.logits(x)
         S, B = y.shape
-        ce = F.cross_entropy(logits.reshape(S * B, -1), y.reshape(-1).long(), reduction="none")
+        ce = misc_ops.softmax_cross_entropy(logits.reshape(S * B, -1), y.reshape(-1))      # one fused fwd+bwd kernel
         return ce.view(S, B).mean(dim=1)

@@ -1,8 +1,8 @@
 """Segmented gradient quantization over a flat arena.
 
 ``quantize_segments_`` = the reference transform (``extensions/quantization/quant.py:9-50``) applied per
-tensor segment.  CUDA path: ``csrc/quant_kernels.cu`` (segmented min/max/abs-quantile by 2-pass radix
-select on the float bit pattern, then a fused encode kernel).  ``pack_segments`` / ``unpack_add_`` are the
+tensor segment.  CUDA path: ``csrc/misc_kernels.cu`` (segmented min/max kernel + fused encode kernel; the
+|g| quantile of each segment comes from ``torch.quantile``).  ``pack_segments`` / ``unpack_add_`` are the
 real wire format: ``bits``-wide level codes + a 1-bit/elem keep mask + (lo, hi) per segment.
 """
 from typing import Sequence, Tuple
@@ -30,9 +30,16 @@ def segment_stats(flat: torch.Tensor, segments, quant_threshold: float, global_s
 
 
 def quantize_segments_(flat: torch.Tensor, segments, quant_bits: int, quant_threshold: float, global_stats=False):
-    if _ext.use_cuda_kernels(flat) and not global_stats:
-        tab = _seg_table(segments, flat.device)
-        _ext.load().quantize_segments(flat, tab, int(quant_bits), float(quant_threshold))
+    """In-place simulated quantization.  CUDA (``csrc/misc_kernels.cu``): segmented min/max in one pass over the arena
+    (ordered-int atomics), |g| quantiles per segment from ``torch.quantile`` (sort-based, exact like the reference),
+    then ONE encode kernel over the whole arena driven by the segment table."""
+    if _ext.use_cuda_kernels(flat) and not global_stats and flat.is_contiguous() and flat.dtype == torch.float32:
+        ext = _ext.load()
+        tab = _seg_table(segments, flat.device).contiguous()
+        stats = ext.seg_minmax(flat.view(-1), tab)
+        segs = segments.tolist() if torch.is_tensor(segments) else list(segments)
+        stats[:, 2] = torch.stack([_abs_quantile(flat[o:o + n], quant_threshold) for o, n in segs])
+        ext.quantize_segments(flat.view(-1), tab, stats, int(quant_bits), False)
         _ext.count_launch(3)
         return flat
     from ..extensions.quantization.quant import quantize_tensor_
@@ -41,6 +48,14 @@ def quantize_segments_(flat: torch.Tensor, segments, quant_bits: int, quant_thre
     for i, (o, n) in enumerate(segs):
         quantize_tensor_(flat[o:o + n], quant_bits, quant_threshold, tuple(stats[i]))
     return flat
+
+
+def _abs_quantile(x: torch.Tensor, q: float) -> torch.Tensor:
+    a = x.reshape(-1).abs()
+    if a.numel() > 2 ** 24:       # torch.quantile's input limit; kthvalue has none
+        k = min(max(int(round(q * (a.numel() - 1))) + 1, 1), a.numel())
+        return a.kthvalue(k).values
+    return torch.quantile(a, q)
 
 
 def pack_segments(flat: torch.Tensor, segments, quant_bits: int, quant_threshold: float):

@@ -406,12 +406,23 @@ def scrub_empty_clients(data_strct):
 
 
 def compute_grad_cosines(grads, model_grad):
-    """cos(g_k, G) per client; one flat dot product per client (ref. ``utils.py:585-595``)."""
-    G = torch.cat([g.detach().reshape(-1).float().cpu() for g in model_grad])
+    """cos(g_k, G) per client (ref. ``utils.py:585-595``).  CUDA inputs: one fused kernel per client
+    (``ops.misc_ops.cosine_stats``: dot and both norms in one pass, nothing copied to the host); the whole list is
+    read back once."""
+    def flat(ts):
+        ts = list(ts) if not torch.is_tensor(ts) else [ts]
+        return ts[0].detach().reshape(-1).float() if len(ts) == 1 else torch.cat([t.detach().reshape(-1).float() for t in ts])
+
+    G = flat(model_grad)
+    if G.is_cuda:
+        from ..ops import misc_ops
+        cos = [misc_ops.cosine(flat(g).to(G.device), G) for g in grads]
+        return [float(c) for c in torch.stack(cos).cpu()] if cos else []
+    G = G.cpu()
     Gn = G.norm()
     out = []
     for g in grads:
-        f = torch.cat([x.detach().reshape(-1).float().cpu() for x in g])
+        f = flat(g).cpu()
         fn = f.norm()
         out.append(float(torch.dot(f, G) / (fn * Gn)) if fn > 0 and Gn > 0 else 0)
     return out

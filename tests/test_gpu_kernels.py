@@ -403,3 +403,81 @@ def test_rnn_cells_match_reference():
     want = torch.autograd.grad((hr, cr), (gates, c), (gh_, gc_))
     for a, b in zip(got, want):
         assert torch.allclose(a, b, atol=1e-4), (a - b).abs().max()
+
+
+# ------------------------------------------------------------------------------------------------ misc kernels (K7/K14/K15/K19)
+def test_quantize_segments_kernel_matches_reference_transform():
+    _ext()
+    from msrflute_b200.ops import quant_ops
+    from msrflute_b200.extensions.quantization.quant import quantize_tensor_
+    torch.manual_seed(11)
+    segs = [(0, 1000), (1024, 37), (1088, 70000), (71104, 1)]          # gaps = alignment padding, must stay untouched
+    flat = torch.randn(71200, device="cuda")
+    flat[1000:1024] = 7.0
+    ref = flat.clone()
+    for o, n in segs:
+        quantize_tensor_(ref[o:o + n], 6, 0.7)
+    got = quant_ops.quantize_segments_(flat.clone(), segs, 6, 0.7)
+    assert torch.equal(got[1000:1024], ref[1000:1024])                  # padding untouched
+    mism = (got - ref).abs() > 1e-5
+    assert mism.float().mean().item() < 1e-4, mism.float().mean()       # (ties at a level boundary may round differently)
+    for o, n in segs[:3]:
+        assert abs((got[o:o + n] == 0).float().mean().item() - (ref[o:o + n] == 0).float().mean().item()) < 2e-3
+
+
+def test_local_dp_kernel_clip_and_noise():
+    _ext()
+    from msrflute_b200.ops import misc_ops
+    torch.manual_seed(12)
+    g = torch.randn(1_000_003, device="cuda") * 3
+    n0 = g.norm().item()
+    h = g.clone()
+    norm = misc_ops.local_dp_(h, 2.0, 0.0, True)
+    assert abs(norm.item() - n0) < 1e-2 * n0 and abs(h.norm().item() - 2.0) < 1e-3
+    small = torch.randn(1000, device="cuda") * 1e-3
+    keep = small.clone()
+    misc_ops.local_dp_(small, 2.0, 0.0, True)
+    assert torch.allclose(small, keep)                                   # below the bound: untouched
+    h = g.clone()
+    misc_ops.local_dp_(h, 2.0, 0.5, False, seed=1234)
+    noise = h - g * (2.0 / n0)
+    assert abs(noise.mean().item()) < 5e-3 and abs(noise.std().item() - 0.5) < 5e-3
+    h2 = g.clone()
+    misc_ops.local_dp_(h2, 2.0, 0.5, False, seed=1234)
+    assert torch.equal(h, h2)                                            # counter-based noise: reproducible
+    h3 = g.clone()
+    misc_ops.local_dp_(h3, 2.0, 0.5, False, seed=1235)
+    assert not torch.equal(h, h3)
+
+
+@pytest.mark.parametrize("shape", [(200, 1000), (7, 10), (33, 62), (64, 4097)])
+def test_softmax_ce_kernel_matches_torch(shape):
+    _ext()
+    from msrflute_b200.ops import misc_ops
+    torch.manual_seed(13)
+    rows, C = shape
+    x = (torch.randn(rows, C, device="cuda") * 4).requires_grad_(True)
+    t = torch.randint(0, C, (rows,), device="cuda")
+    t[0] = -100
+    wts = torch.rand(rows, device="cuda")
+    loss = misc_ops.softmax_cross_entropy(x, t)
+    (loss * wts).sum().backward()
+    x2 = x.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(x2, t, reduction="none", ignore_index=-100)
+    (ref * wts).sum().backward()
+    assert torch.allclose(loss, ref, atol=2e-5, rtol=1e-5), (loss - ref).abs().max()
+    assert torch.allclose(x.grad, x2.grad, atol=2e-6, rtol=1e-4), (x.grad - x2.grad).abs().max()
+
+
+def test_cosine_stats_kernel():
+    _ext()
+    from msrflute_b200.ops import misc_ops
+    torch.manual_seed(14)
+    a, b = torch.randn(3_000_001, device="cuda"), torch.randn(3_000_001, device="cuda")
+    s = misc_ops.cosine_stats(a, b)
+    ref = torch.stack([torch.dot(a.double(), b.double()), torch.dot(a.double(), a.double()), torch.dot(b.double(), b.double())]).float()
+    assert torch.allclose(s, ref, rtol=1e-4, atol=1.0), (s, ref)
+    assert abs(misc_ops.cosine(a, 2 * a).item() - 1.0) < 1e-5
+    from msrflute_b200.utils import compute_grad_cosines
+    cs = compute_grad_cosines([[a[:100], a[100:]], [b]], [a])
+    assert abs(cs[0] - 1.0) < 1e-5 and abs(cs[1] - (ref[0] / (ref[1] * ref[2]).sqrt()).item()) < 1e-4
