@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(kThreads) seg_minmax_kernel(const float* __res
   while (pos < end) {
     const int s = find_segment(seg, nseg, pos);
     const long long so = seg[2 * s], se = so + seg[2 * s + 1];
+    if (pos >= se) break;                                    // past the last tensor (tail padding)
     if (pos < so) { pos = so; continue; }                    // padding between tensors
     if (so >= end) break;
     const long long stop = min(end, se);

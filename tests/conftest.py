@@ -17,6 +17,16 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
+        # A kernel that never terminates blocks the host in a CUDA sync where no Python-level timeout can fire:
+        # bound every GPU test with pytest-timeout's thread method (dumps stacks, then os._exit) so one bad kernel
+        # costs minutes, not the whole GPU budget.
+        try:
+            import pytest_timeout  # noqa: F401
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(240, method="thread"))
+        except ImportError:
+            pass
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

@@ -444,10 +444,11 @@ def test_local_dp_kernel_clip_and_noise():
     assert abs(noise.mean().item()) < 5e-3 and abs(noise.std().item() - 0.5) < 5e-3
     h2 = g.clone()
     misc_ops.local_dp_(h2, 2.0, 0.5, False, seed=1234)
-    assert torch.equal(h, h2)                                            # counter-based noise: reproducible
+    assert (h - h2).abs().max().item() < 1e-5                            # counter-based noise: reproducible (the norm's
+                                                                         # atomic reduction order may change the last bit)
     h3 = g.clone()
     misc_ops.local_dp_(h3, 2.0, 0.5, False, seed=1235)
-    assert not torch.equal(h, h3)
+    assert (h - h3).abs().max().item() > 0.1
 
 
 @pytest.mark.parametrize("shape", [(200, 1000), (7, 10), (33, 62), (64, 4097)])
