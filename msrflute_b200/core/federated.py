@@ -302,6 +302,17 @@ def _finish_deferred(comm, worker, local, n_clients):
     return DeferredRound(n_clients, wsum[0], resolve)
 
 
+def _maybe_inject_fault(rank, nround):
+    """Fault injection for failure-detection tests: ``FLUTE_FAULT_INJECT=<rank>:<round>`` makes that worker die
+    (``os._exit(17)``) when it receives the command of that round."""
+    spec = os.environ.get("FLUTE_FAULT_INJECT", "")
+    if spec:
+        r, n = spec.split(":")
+        if int(r) == rank and int(n) == int(nround):
+            print_rank("fault injection: rank {} exits at round {}".format(rank, nround), logging.WARNING)
+            os._exit(17)
+
+
 def _strip(o):
     """Client record without the (device) gradient payload — what travels on the control plane."""
     rec = {k: v for k, v in o.items() if k != "pl"}
@@ -452,6 +463,7 @@ class Worker:
             elif ctrl["sync"] == "list":
                 self.set_weights(comm.bcast_object(None, src=0))
             mine = ctrl["assign"].get(comm.rank, [])
+            _maybe_inject_fault(comm.rank, ctrl.get("round", -1))
             if cmd == COMMAND_TRAIN:
                 if ctrl.get("defer"):
                     res = self.train_clients(mine, (ctrl["lr"], None, ctrl["round"]), fused=True,

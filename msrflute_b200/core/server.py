@@ -188,6 +188,8 @@ class OptimizationServer(federated.Server):
     # The three phases of ``train`` are public so callers (bench.py, notebooks) can step rounds themselves.
     def begin_training(self):
         """Initial evaluation + the initial checkpoint dump (ref. ``server.py:232-255``)."""
+        from ..utils.timing import RoundTimer, TraceWindow
+        self._round_timer, self._trace = RoundTimer(), TraceWindow()
         self.run_stats = {k: [] for k in (
             "secsPerClientRound", "secsPerClient", "secsPerClientTraining", "secsPerClientSetup",
             "secsPerClientFull", "secsPerRoundHousekeeping", "secsPerRoundTotal", "communicationCosts")}
@@ -219,11 +221,15 @@ class OptimizationServer(federated.Server):
 
     def end_training(self):
         from ..utils.async_ckpt import flush_checkpoints
+        if getattr(self, "_trace", None) is not None:
+            self._trace.close()
         flush_checkpoints()
         self.terminate_workers(terminate=(not self.do_clustering))
 
     def _train_round(self, i, eval_list):
         begin = time.time()
+        if getattr(self, "_trace", None) is not None:
+            self._trace.step(i)
         metrics_payload = {}
 
         def log_metric(k, v):
@@ -437,6 +443,10 @@ class OptimizationServer(federated.Server):
                 log_metric(f"{metric}Mean", float(np.mean(vals)))
                 log_metric(f"{metric}Median", float(np.median(vals)))
                 log_metric(f"{metric}Max", float(max(vals)))
+        if getattr(self, "_round_timer", None) is not None:      # device time of completed rounds (never blocks)
+            self._round_timer.mark(i)
+            for r, ms in self._round_timer.drain():
+                run.log("devMsPerRound", ms)
         for k, v in metrics_payload.items():
             run.log(k, v)
         for hook in self.round_hooks:

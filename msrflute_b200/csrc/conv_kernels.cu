@@ -626,11 +626,21 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
 }
 
 static int pick_splits_tc(long long tiles, int stages) {
-  const long long target = 148LL * 2;              // two CTAs (2 x 98 KB smem, 2 x 64 TMEM columns) are resident per SM
-  if (tiles >= target || stages < 4) return 1;
-  long long s = (target + tiles - 1) / tiles;
-  s = std::min<long long>(s, stages / 2);
-  return static_cast<int>(std::max<long long>(1, std::min<long long>(s, 32)));
+  // These launches are latency-bound: a CTA costs a fixed prologue/epilogue (barriers, TMEM allocation, tap masks,
+  // accumulator read-out) plus ~1.2 us per 32-deep stage, and 2 CTAs are resident per SM (2 x 98 KB smem).  Splitting the
+  // reduction shortens the per-CTA chain but a grid of 300 CTAs on 296 slots runs as TWO waves; pick the split count that
+  // minimises  waves x (fixed + stages_per_cta x stage)  (+ the zero-fill / atomic combine when splitting at all).
+  const double fixed_us = 5.0, stage_us = 1.2, combine_us = 1.5;
+  const long long slots = 148LL * 2;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= std::min(32, std::max(1, stages)); ++s) {
+    const long long waves = (tiles * s + slots - 1) / slots;
+    const int per = (stages + s - 1) / s;
+    const double cost = static_cast<double>(waves) * (fixed_us + per * stage_us) + (s > 1 ? combine_us : 0.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return best;
 }
 
 template <int MODE>

@@ -90,7 +90,9 @@ class CollectiveComm(Communicator):
             device = torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu")
         self.device = device
         # CPU-side control group: object collectives never touch the GPU stream
-        self.ctrl_group = dist.new_group(backend="gloo") if self.backend != "gloo" else dist.group.WORLD
+        import datetime
+        timeout = datetime.timedelta(seconds=float(os.environ.get("FLUTE_COMM_TIMEOUT_S", "1800")))
+        self.ctrl_group = dist.new_group(backend="gloo", timeout=timeout) if self.backend != "gloo" else dist.group.WORLD
 
     def bcast_object(self, obj, src=0):
         box = [obj]
@@ -152,12 +154,16 @@ def init_distributed(backend: Optional[str] = None):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        # Failure detection (the reference blocks forever on a dead peer): every collective / control
+        # message carries this timeout, so a rank whose peer died raises instead of hanging the job.
+        import datetime
+        timeout = datetime.timedelta(seconds=float(os.environ.get("FLUTE_COMM_TIMEOUT_S", "1800")))
         if backend == "nccl":
             torch.cuda.set_device(env_local_rank())
-            dist.init_process_group(backend="nccl", rank=env_rank(), world_size=ws,
+            dist.init_process_group(backend="nccl", rank=env_rank(), world_size=ws, timeout=timeout,
                                     device_id=torch.device("cuda", env_local_rank()))
         else:
-            dist.init_process_group(backend=backend, rank=env_rank(), world_size=ws)
+            dist.init_process_group(backend=backend, rank=env_rank(), world_size=ws, timeout=timeout)
     elif torch.cuda.is_available():
         torch.cuda.set_device(env_local_rank() if env_local_rank() < torch.cuda.device_count() else 0)
     return env_rank(), ws

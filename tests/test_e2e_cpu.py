@@ -142,3 +142,24 @@ def test_two_ranks_gloo_deferred_round_protocol(tmp_path):
     m = _metrics(exp)
     assert m["Val loss"][-1] < m["Val loss"][0]
     assert len(m["Training loss"]) == 3
+
+
+def test_dead_worker_is_detected_not_hung(tmp_path):
+    """in the reference a dead worker hangs the job forever.  Here every control message / collective has
+    a timeout and the launcher tears the job down: a worker killed by fault injection at round 1 makes the whole run
+    exit non-zero within seconds."""
+    import time
+    tmp = str(tmp_path)
+    _write_data(tmp)
+    out = os.path.join(tmp, "out")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29619", os.path.join(ROOT, "e2e_trainer.py"), "-config",
+           _config(tmp, rounds=50), "-outputPath", out, "-dataPath", tmp, "-task", "cv_lr_mnist", "-backend", "gloo",
+           "-experiment", "exp"]
+    env = dict(os.environ, PYTHONPATH=ROOT, FLUTE_ALLOW_FALLBACK="1", CUDA_VISIBLE_DEVICES="",
+               FLUTE_FAULT_INJECT="1:1", FLUTE_COMM_TIMEOUT_S="20")
+    t0 = time.time()
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0
+    assert time.time() - t0 < 120
+    assert "fault injection: rank 1 exits at round 1" in (r.stdout + r.stderr)

@@ -284,19 +284,24 @@ def _check_slot_conv(cfg, tf32):
     y.backward(dy)
     torch.backends.cudnn.allow_tf32 = False
     for s in range(S):
-        w = W[s, off:off + n].view(Cout, Cin, k, k).clone().requires_grad_(True)
-        xs = x[s].detach().clone().requires_grad_(True)
-        ys = torch.nn.functional.conv2d(xs, w, None, stride, pad)
-        ys.backward(dy[s])
-        gw = G[s, off:off + n].view_as(w)
+        # reference in float64: cuDNN's fp32 algorithm choice (FFT / Winograd variants) is itself only ~1e-3 accurate
+        # for some shapes, which made the exact-fp32 comparison depend on its autotuner
+        w64 = W[s, off:off + n].view(Cout, Cin, k, k).double().requires_grad_(True)
+        xs64 = x[s].detach().double().requires_grad_(True)
+        ys64 = torch.nn.functional.conv2d(xs64, w64, None, stride, pad)
+        ys64.backward(dy[s].double())
+        ys, w, xs = ys64.float(), w64, xs64
+
+        wg, xg = w64.grad.float(), xs64.grad.float()
+        gw = G[s, off:off + n].view(Cout, Cin, k, k)
         if tf32:        # 10-bit mantissa operands, fp32 accumulation: bound the error by the size of the result
-            for got, ref in ((y[s], ys), (x.grad[s], xs.grad), (gw, w.grad)):
+            for got, ref in ((y[s], ys), (x.grad[s], xg), (gw, wg)):
                 err = (got - ref).abs().max().item()
                 assert err <= 4e-3 * ref.abs().max().item() + 1e-5, (err, ref.abs().max().item())
             continue
         assert torch.allclose(y[s], ys, atol=2e-3, rtol=1e-3), (y[s] - ys).abs().max()
-        assert torch.allclose(x.grad[s], xs.grad, atol=2e-3, rtol=1e-3), (x.grad[s] - xs.grad).abs().max()
-        assert torch.allclose(gw, w.grad, atol=5e-3, rtol=2e-3), (gw - w.grad).abs().max()
+        assert torch.allclose(x.grad[s], xg, atol=2e-3, rtol=1e-3), (x.grad[s] - xg).abs().max()
+        assert torch.allclose(gw, wg, atol=5e-3, rtol=2e-3), (gw - wg).abs().max()
     assert G[:, :off].abs().sum() == 0 and G[:, off + n:].abs().sum() == 0         # nothing written outside the tensor
 
 
