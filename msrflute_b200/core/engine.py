@@ -141,10 +141,23 @@ class DeviceClientEngine:
         self.layout: ArenaLayout = ar[0].layout
         P = self.layout.padded_numel
         dev = self.device
+        opt = self.config["client_config"]["optimizer_config"]
+        self.weight_decay = float(opt.get("weight_decay", 0.0) or 0.0)
+        self._pack_dataset()
+        self.slot_plan = self._plan_compact_slots(base)
+        if self.slot_plan is not None:
+            # compact slot arenas: only live parameters exist per client (see SlotBatchedResNet.plan_compact); the
+            # per-slot nn.Modules of the generic fallback cannot alias such rows, so this mode is lock-step only
+            P = int(self.slot_plan["numel"])
+            self.index_map = self.slot_plan["index_map"].to(dev)
+            print_rank("device engine: compact slot arenas, {} of {} parameters live per client ({} filters pruned)".format(
+                int((self.index_map >= 0).sum()), self.layout.numel, len(self.slot_plan["compact"])), logging.INFO)
+        else:
+            self.index_map = None
         self.W = torch.zeros(self.S, P, device=dev)
         self.G = torch.zeros(self.S, P, device=dev)
         self.slots: List[_Slot] = []
-        for s in range(self.S):
+        for s in range(self.S if self.slot_plan is None else 0):
             m = copy.deepcopy(base)
             for attr in ("_flute_arena", "_flute_client_ctx"):
                 if hasattr(m, attr):
@@ -163,31 +176,57 @@ class DeviceClientEngine:
         self.first = torch.ones(self.S, dtype=torch.int32, device=dev) if self.momentum != 0 else None
         self.nesterov = bool(opt.get("nesterov", False))
         self.dampening = float(opt.get("dampening", 0.0) or 0.0)
-        self.weight_decay = float(opt.get("weight_decay", 0.0) or 0.0)
-        self._pack_dataset()
         # stacked (strided) per-parameter views over the slot arenas for the vmapped step
         names = [n for n, _ in base.named_parameters()]
         lay = self.layout
-        self.param_stack = {"m." + n: self.W[:, o:o + k].view((self.S,) + tuple(sh))
-                            for n, o, k, sh in zip(names, lay.offsets, lay.sizes, lay.shapes)}
-        self.grad_stack = [self.G[:, o:o + k].view((self.S,) + tuple(sh))
-                           for o, k, sh in zip(lay.offsets, lay.sizes, lay.shapes)]
-        self.param_names = ["m." + n for n in names]
         self.has_buffers = any(True for _ in base.buffers())
-        self.loss_module = _LossModule(self.slots[0].model)
         self.slot_model = None
-        if self.device.type == "cuda" and self.want_wave:
+        if self.slot_plan is not None:
             from ..models.slot_resnet import SlotBatchedResNet
-            ext = _ext.load()
-            if ext is not None and hasattr(ext, "slot_conv_fprop") and SlotBatchedResNet.supports(base):
-                self.slot_model = SlotBatchedResNet(self.slots[0].model, self.layout, self.W, self.G)
-                print_rank("device engine: slot-batched hand-written conv/GroupNorm path enabled", logging.INFO)
+            self.slot_model = SlotBatchedResNet(base, self.layout, self.W, self.G, plan=self.slot_plan)
+            self.param_stack, self.grad_stack, self.param_names, self.loss_module = {}, [], [], None
+            print_rank("device engine: slot-batched hand-written conv/GroupNorm path enabled", logging.INFO)
+        else:
+            self.param_stack = {"m." + n: self.W[:, o:o + k].view((self.S,) + tuple(sh))
+                                for n, o, k, sh in zip(names, lay.offsets, lay.sizes, lay.shapes)}
+            self.grad_stack = [self.G[:, o:o + k].view((self.S,) + tuple(sh))
+                               for o, k, sh in zip(lay.offsets, lay.sizes, lay.shapes)]
+            self.param_names = ["m." + n for n in names]
+            self.loss_module = _LossModule(self.slots[0].model)
+            if self.device.type == "cuda" and self.want_wave:
+                from ..models.slot_resnet import SlotBatchedResNet
+                ext = _ext.load()
+                if ext is not None and hasattr(ext, "slot_conv_fprop") and SlotBatchedResNet.supports(base):
+                    self.slot_model = SlotBatchedResNet(self.slots[0].model, self.layout, self.W, self.G)
+                    print_rank("device engine: slot-batched hand-written conv/GroupNorm path enabled", logging.INFO)
         self.wave_graphs: Dict[tuple, object] = {}
         self.wave_static: Dict[tuple, dict] = {}
         self._staging: Dict[tuple, list] = {}
         self.wave_kernels: Dict[tuple, int] = {}
         self.wave_pool = None
         self._built = True
+
+    def _plan_compact_slots(self, base):
+        """Compact slot arenas are used when (a) the model has a slot-batched executor, (b) no weight decay touches
+        parameters whose gradient is structurally zero, (c) every client runs the same number of full batches (all slots
+        stay in lock-step, the per-slot fallback is never needed)."""
+        import os as _os
+        if self.device.type != "cuda" or not self.want_wave or _os.environ.get("FLUTE_COMPACT_SLOTS", "1") == "0":
+            return None
+        if self.weight_decay != 0.0:
+            return None
+        from ..models.slot_resnet import SlotBatchedResNet
+        ext = _ext.load()
+        if ext is None or not hasattr(ext, "slot_scatter_in") or not SlotBatchedResNet.supports(base):
+            return None
+        dcfg = self.config["client_config"]["data_config"]["train"]
+        bs = int(dcfg["batch_size"])
+        sizes = set(int(self.offsets[i + 1] - self.offsets[i]) for i in range(len(self.offsets) - 1))
+        if len(sizes) != 1 or next(iter(sizes)) % bs != 0:
+            return None
+        src = self.X if self.resident else self.Xh
+        example = self.dataset.transform_batch(src[:2].to(self.device))
+        return SlotBatchedResNet.plan_compact(base, self.layout, example)
 
     def _pack_dataset(self):
         """One contiguous (pinned) pack of every user's raw samples + per-user offsets; uploaded once if resident."""
@@ -379,7 +418,10 @@ class DeviceClientEngine:
         for wave_start in range(0, len(client_ids), self.S):
             wave = client_ids[wave_start:wave_start + self.S]
             n_act = len(wave)
-            self.W.copy_(w_global.view(1, -1).expand(self.S, -1))      # the "broadcast" into every slot
+            if self.index_map is not None:
+                arena_ops.scatter_in(self.W, w_global, self.index_map)  # the "broadcast" into every (compact) slot
+            else:
+                self.W.copy_(w_global.view(1, -1).expand(self.S, -1))   # the "broadcast" into every slot
             self.stats.zero_()
             self.loss_sum.zero_()
             if self.first is not None:
@@ -412,6 +454,9 @@ class DeviceClientEngine:
                     b0 = b + 1
                     for s in range(n_act):
                         ns_done[s] += bs
+            if b0 < max(nbs) and self.slot_plan is not None:
+                raise RuntimeError("compact slot arenas require lock-step clients (equal shard sizes, full batches); "
+                                   "set FLUTE_COMPACT_SLOTS=0")
             if b0 < max(nbs):
                 # per-slot path for whatever could not run in lock-step
                 if main is not None:
@@ -450,7 +495,10 @@ class DeviceClientEngine:
             act[:n_act] = 1
             self.active.copy_(act.to(dev, non_blocking=True))
             self.weights.copy_(w * self.active.float())
-            arena_ops.accumulate_pseudo_grad(acc, w_global, self.W, self.weights, self.active)
+            if self.index_map is not None:
+                arena_ops.accumulate_pseudo_grad_mapped(acc, w_global, self.W, self.weights, self.active, self.index_map)
+            else:
+                arena_ops.accumulate_pseudo_grad(acc, w_global, self.W, self.weights, self.active)
             rec = records[wave_start:wave_start + n_act]
             rec[:, REC_LOSS] = self.loss_sum[:n_act]
             rec[:, REC_SUM:REC_COUNT + 1] = self.stats[:n_act, 0:3]

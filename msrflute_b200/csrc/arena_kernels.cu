@@ -238,6 +238,66 @@ accumulate_pg_kernel(float* __restrict__ acc, const float* __restrict__ wg, cons
   }
 }
 
+// ---- compact slot arenas -------------------------------------------------------------------------------------------
+// A slot arena may hold only the LIVE elements of the model (filter taps that can only ever see zero padding have
+// identically zero gradients, so with weight_decay == 0 they never change and need not exist per client).
+// map[j] = index of slot element j in the global arena, -1 for alignment padding.
+__global__ void __launch_bounds__(kThreads)
+slot_scatter_in_kernel(float* __restrict__ W, int64_t Pc, int S, const float* __restrict__ wg, const int* __restrict__ map) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  for (int64_t j = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; j < Pc; j += stride) {
+    const int m = map[j];
+    const float v = m >= 0 ? __ldg(wg + m) : 0.f;
+    for (int s = 0; s < S; ++s) W[static_cast<int64_t>(s) * Pc + j] = v;
+  }
+}
+
+// acc[map[j]] += sum_s wts[s] * active[s] * (wg[map[j]] - wl[s][j])      (map is injective: no atomics)
+__global__ void __launch_bounds__(kThreads)
+accumulate_pg_mapped_kernel(float* __restrict__ acc, const float* __restrict__ wg, const float* __restrict__ wl, int64_t Pc,
+                            int S, const float* __restrict__ wts, const int* __restrict__ active, const int* __restrict__ map) {
+  extern __shared__ float s_w[];
+  for (int s = threadIdx.x; s < S; s += blockDim.x) s_w[s] = (active == nullptr || active[s] != 0) ? wts[s] : 0.f;
+  __syncthreads();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  for (int64_t j = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; j < Pc; j += stride) {
+    const int m = map[j];
+    if (m < 0) continue;
+    const float x = __ldg(wg + m);
+    float r = acc[m];
+    for (int s = 0; s < S; ++s) {
+      const float wt = s_w[s];
+      if (wt != 0.f) r = fmaf(wt, x - wl[static_cast<int64_t>(s) * Pc + j], r);
+    }
+    acc[m] = r;
+  }
+}
+
+void slot_scatter_in(torch::Tensor W, torch::Tensor wg, torch::Tensor map) {
+  check_rows(W, "W");
+  TORCH_CHECK(map.is_cuda() && map.scalar_type() == torch::kInt32 && map.numel() == W.size(1) && wg.is_cuda() &&
+              wg.scalar_type() == torch::kFloat32, "slot_scatter_in: int32 map of the slot row length expected");
+  const c10::cuda::CUDAGuard guard(W.device());
+  const int64_t Pc = W.size(1);
+  slot_scatter_in_kernel<<<blocks_for(Pc), kThreads, 0, at::cuda::getCurrentCUDAStream()>>>(
+      W.data_ptr<float>(), Pc, static_cast<int>(W.size(0)), wg.data_ptr<float>(), map.data_ptr<int>());
+  FLUTE_CUDA_CHECK(cudaGetLastError());
+}
+
+void accumulate_pseudo_grad_mapped(torch::Tensor acc, torch::Tensor wg, torch::Tensor wl, torch::Tensor weights,
+                                   c10::optional<torch::Tensor> active, torch::Tensor map) {
+  check_rows(wl, "w_local");
+  const int S = static_cast<int>(wl.size(0));
+  const int64_t Pc = wl.size(1);
+  TORCH_CHECK(map.is_cuda() && map.scalar_type() == torch::kInt32 && map.numel() == Pc && acc.numel() == wg.numel() &&
+              weights.numel() == S && weights.scalar_type() == torch::kFloat32);
+  const c10::cuda::CUDAGuard guard(acc.device());
+  accumulate_pg_mapped_kernel<<<blocks_for(Pc), kThreads, S * sizeof(float), at::cuda::getCurrentCUDAStream()>>>(
+      acc.data_ptr<float>(), wg.data_ptr<float>(), wl.data_ptr<float>(), Pc, S, weights.data_ptr<float>(),
+      active.has_value() ? active->data_ptr<int>() : nullptr, map.data_ptr<int>());
+  FLUTE_CUDA_CHECK(cudaGetLastError());
+}
+
 void accumulate_pseudo_grad(torch::Tensor acc, torch::Tensor wg, torch::Tensor wl, torch::Tensor weights,
                             c10::optional<torch::Tensor> active) {
   check_rows(wl, "w_local");

@@ -41,12 +41,15 @@ std::vector<torch::Tensor> group_norm_bwd_arena(torch::Tensor dy, torch::Tensor 
                                                 int64_t G, bool relu, bool per_group_affine, bool has_residual,
                                                 int64_t sets, torch::Tensor g_arena, int64_t gw_off, int64_t gb_off);
 at::Tensor slot_conv_fprop(at::Tensor x, at::Tensor w_arena, int64_t w_offset, int64_t Cout, int64_t KH, int64_t KW,
-                           int64_t stride, int64_t pad);
+                           int64_t stride, int64_t pad, bool compact);
 at::Tensor slot_conv_dgrad(at::Tensor dy, at::Tensor w_arena, int64_t w_offset, int64_t Cin, int64_t Hi, int64_t Wi,
-                           int64_t KH, int64_t KW, int64_t stride, int64_t pad);
+                           int64_t KH, int64_t KW, int64_t stride, int64_t pad, bool compact);
 void slot_conv_wgrad(at::Tensor x, at::Tensor dy, at::Tensor g_arena, int64_t g_offset, int64_t KH, int64_t KW,
-                     int64_t stride, int64_t pad);
+                     int64_t stride, int64_t pad, bool compact);
 void slot_conv_set_impl(int64_t impl);
+void slot_scatter_in(torch::Tensor W, torch::Tensor wg, torch::Tensor map);
+void accumulate_pseudo_grad_mapped(torch::Tensor acc, torch::Tensor wg, torch::Tensor wl, torch::Tensor weights,
+                                   c10::optional<torch::Tensor> active, torch::Tensor map);
 at::Tensor seg_minmax(at::Tensor flat, at::Tensor seg);
 std::vector<at::Tensor> quantize_segments(at::Tensor flat, at::Tensor seg, at::Tensor stats, int64_t bits, bool emit_codes);
 at::Tensor local_dp(at::Tensor flat, double max_grad, double sigma, bool clip_only, int64_t seed);
@@ -74,6 +77,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("slot_conv_dgrad", &flute::slot_conv_dgrad);
   m.def("slot_conv_wgrad", &flute::slot_conv_wgrad);
   m.def("slot_conv_set_impl", &flute::slot_conv_set_impl);
+  m.def("slot_scatter_in", &flute::slot_scatter_in);
+  m.def("accumulate_pseudo_grad_mapped", &flute::accumulate_pseudo_grad_mapped);
   m.def("seg_minmax", &flute::seg_minmax);
   m.def("quantize_segments", &flute::quantize_segments);
   m.def("local_dp", &flute::local_dp);

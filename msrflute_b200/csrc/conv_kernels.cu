@@ -36,6 +36,7 @@ struct ConvP {
   int S, B, Cin, Hi, Wi, Cout, Ho, Wo, KH, KW, stride, pad;
   int splits;                 // reduction splits (blockIdx.z = slot * splits + split)
   int ntaps;                  // taps that touch real data for at least one output position
+  int compact;                // 1: the weight tensor stores ONLY the live taps, [Cout, Cin, ntaps] (compact slot arenas)
   long long w_slot_stride;    // floats between two slots' copies of this weight tensor (= arena row length P)
   unsigned short taps[MAX_TAPS];   // kh << 8 | kw
 };
@@ -62,7 +63,8 @@ __global__ void __launch_bounds__(THREADS) conv_fprop_kernel(const float* __rest
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int slot = blockIdx.z / p.splits, split = blockIdx.z - slot * p.splits;
-  const int M = p.B * p.Ho * p.Wo, N = p.Cout, KHW = p.KH * p.KW, K = p.Cin * p.ntaps, Kfull = p.Cin * KHW;
+  const int M = p.B * p.Ho * p.Wo, N = p.Cout, KHW = p.KH * p.KW, K = p.Cin * p.ntaps;
+  const int Kfull = p.compact ? K : p.Cin * KHW;       // row pitch of the stored filter
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int kchunks = (K + BK - 1) / BK;
   const int per = (kchunks + p.splits - 1) / p.splits;
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(THREADS) conv_fprop_kernel(const float* __rest
     int woff = -1;
     if (kb < K) {
       const int ci = kb / p.ntaps, t = p.taps[kb - ci * p.ntaps];
-      woff = ci * KHW + (t >> 8) * p.KW + (t & 255);
+      woff = p.compact ? kb : ci * KHW + (t >> 8) * p.KW + (t & 255);
     }
 #pragma unroll
     for (int pass = 0; pass < 4; ++pass) {
@@ -167,7 +169,8 @@ __global__ void __launch_bounds__(THREADS) conv_dgrad_kernel(const float* __rest
       tw0 = iw + p.pad;
     }
   }
-  const int CinKHW = p.Cin * KHW;
+  const int wtaps = p.compact ? p.ntaps : KHW;         // taps stored per (co, ci)
+  const int CinKHW = p.Cin * wtaps;
   float ra[4], rb[4];
   auto load_chunk = [&](int kc) {
     const int k0 = kc * BK;
@@ -190,13 +193,13 @@ __global__ void __launch_bounds__(THREADS) conv_dgrad_kernel(const float* __rest
     const int kb = k0 + b_k;
     long long woff = -1;
     if (kb < K) {
-      const int co = kb / p.ntaps, t = p.taps[kb - co * p.ntaps];
-      woff = static_cast<long long>(co) * CinKHW + (t >> 8) * p.KW + (t & 255);
+      const int co = kb / p.ntaps, ti = kb - co * p.ntaps, t = p.taps[ti];
+      woff = static_cast<long long>(co) * CinKHW + (p.compact ? ti : (t >> 8) * p.KW + (t & 255));
     }
 #pragma unroll
     for (int pass = 0; pass < 4; ++pass) {
       const int ci = n0 + b_n + pass * 16;
-      rb[pass] = (woff >= 0 && ci < N) ? __ldg(ws + woff + static_cast<long long>(ci) * KHW) : 0.f;
+      rb[pass] = (woff >= 0 && ci < N) ? __ldg(ws + woff + static_cast<long long>(ci) * wtaps) : 0.f;
     }
   };
   if (kc_begin < kc_end) load_chunk(kc_begin);
@@ -234,7 +237,8 @@ __global__ void __launch_bounds__(THREADS) conv_wgrad_kernel(const float* __rest
   __shared__ __align__(16) float As[BK][BM + 4];     // dy^T chunk: [m-chunk][co]
   __shared__ __align__(16) float Bs[BK][BN + 4];     // im2col chunk: [m-chunk][k]
   const int slot = blockIdx.z / p.splits, split = blockIdx.z - slot * p.splits;
-  const int M = p.B * p.Ho * p.Wo, KHW = p.KH * p.KW, K = p.Cin * p.ntaps, Kfull = p.Cin * KHW, HoWo = p.Ho * p.Wo;
+  const int M = p.B * p.Ho * p.Wo, KHW = p.KH * p.KW, K = p.Cin * p.ntaps, HoWo = p.Ho * p.Wo;
+  const int Kfull = p.compact ? K : p.Cin * KHW;
   const int co0 = blockIdx.x * BM, k0 = blockIdx.y * BN;
   const int mchunks = (M + BK - 1) / BK;
   const int per = (mchunks + p.splits - 1) / p.splits;
@@ -288,7 +292,7 @@ __global__ void __launch_bounds__(THREADS) conv_wgrad_kernel(const float* __rest
     const int k = k0 + tn * 4 + j;
     if (k >= K) continue;
     const int ci = k / p.ntaps, t = p.taps[k - ci * p.ntaps];
-    const int woff = ci * KHW + (t >> 8) * p.KW + (t & 255);
+    const int woff = p.compact ? k : ci * KHW + (t >> 8) * p.KW + (t & 255);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int co = co0 + tm * 4 + i;
@@ -333,6 +337,7 @@ static ConvP make_params(int64_t S, int64_t B, int64_t Cin, int64_t Hi, int64_t 
   p.Wo = (p.Wi + 2 * p.pad - p.KW) / p.stride + 1;
   p.w_slot_stride = w_slot_stride;
   p.splits = 1;
+  p.compact = 0;
   set_taps(p);
   return p;
 }
@@ -518,13 +523,15 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
           const int kb = r0 + lane;
           long long woff = -1;
           if (kb < RED) {
-            const int cc = kb / p.ntaps;
-            const int2 tp = tap_table[kb - cc * p.ntaps];
-            const int tap_off = (tp.y >> 16) * p.KW + (tp.y & 0xFFFF);
-            woff = MODE == FPROP ? static_cast<long long>(cc) * KHW + tap_off
-                                 : static_cast<long long>(cc) * p.Cin * KHW + tap_off;
+            const int cc = kb / p.ntaps, tib = kb - cc * p.ntaps;
+            const int2 tp = tap_table[tib];
+            const int wtaps = p.compact ? p.ntaps : KHW;                    // taps stored per (co, ci)
+            const int tap_off = p.compact ? tib : (tp.y >> 16) * p.KW + (tp.y & 0xFFFF);
+            woff = MODE == FPROP ? static_cast<long long>(cc) * wtaps + tap_off
+                                 : static_cast<long long>(cc) * p.Cin * wtaps + tap_off;
           }
-          const long long row_pitch = MODE == FPROP ? static_cast<long long>(p.Cin) * KHW : KHW;
+          const long long row_pitch = MODE == FPROP ? static_cast<long long>(p.Cin) * (p.compact ? p.ntaps : KHW)
+                                                    : (p.compact ? p.ntaps : KHW);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int brow = warp * 8 + i, n = c_tile0 + brow;
@@ -575,8 +582,9 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
       if (rr < R) {
         if (MODE == WGRAD) {
           const int ci = rr / p.ntaps, t = p.taps[rr - ci * p.ntaps];
-          float* dst = out + static_cast<long long>(slot) * p.w_slot_stride + ci * KHW + (t >> 8) * p.KW + (t & 255);
-          const long long pitch = static_cast<long long>(p.Cin) * KHW;
+          float* dst = out + static_cast<long long>(slot) * p.w_slot_stride +
+                       (p.compact ? rr : ci * KHW + (t >> 8) * p.KW + (t & 255));
+          const long long pitch = p.compact ? static_cast<long long>(R) : static_cast<long long>(p.Cin) * KHW;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int co = c_tile0 + chalf * 32 + j;
@@ -665,11 +673,12 @@ static bool use_tc(int work_rows) { return g_conv_impl == 2 || (g_conv_impl == 0
 
 // w_arena: the [S, P] parameter arena; the layer's weight of slot s lives at w_arena + s*P + w_offset
 at::Tensor slot_conv_fprop(at::Tensor x, at::Tensor w_arena, int64_t w_offset, int64_t Cout, int64_t KH, int64_t KW,
-                           int64_t stride, int64_t pad) {
+                           int64_t stride, int64_t pad, bool compact) {
   using namespace conv;
   check5(x, "x");
   check_arena(w_arena, x.size(0));
   ConvP p = make_params(x.size(0), x.size(1), x.size(2), x.size(3), x.size(4), Cout, KH, KW, stride, pad, w_arena.size(1));
+  p.compact = compact ? 1 : 0;
   const c10::cuda::CUDAGuard guard(x.device());
   const int M = p.B * p.Ho * p.Wo, K = p.Cin * p.ntaps;
   if (use_tc(M)) {
@@ -677,7 +686,7 @@ at::Tensor slot_conv_fprop(at::Tensor x, at::Tensor w_arena, int64_t w_offset, i
     p.splits = tcv::pick_splits_tc(tiles, (K + tcv::TK - 1) / tcv::TK);
     auto y = p.splits > 1 ? at::zeros({p.S, p.B, p.Cout, p.Ho, p.Wo}, x.options())
                           : at::empty({p.S, p.B, p.Cout, p.Ho, p.Wo}, x.options());
-    const int vec_b = (p.ntaps == p.KH * p.KW) && (K % 4 == 0) && ((w_offset % 4) == 0) && (w_arena.size(1) % 4 == 0);
+    const int vec_b = (p.ntaps == p.KH * p.KW || p.compact) && (K % 4 == 0) && ((w_offset % 4) == 0) && (w_arena.size(1) % 4 == 0);
     tcv::launch_tc<tcv::FPROP>(x.data_ptr<float>(), w_arena.data_ptr<float>() + w_offset, y.data_ptr<float>(), p, M, p.Cout, vec_b);
     return y;
   }
@@ -693,11 +702,12 @@ at::Tensor slot_conv_fprop(at::Tensor x, at::Tensor w_arena, int64_t w_offset, i
 }
 
 at::Tensor slot_conv_dgrad(at::Tensor dy, at::Tensor w_arena, int64_t w_offset, int64_t Cin, int64_t Hi, int64_t Wi,
-                           int64_t KH, int64_t KW, int64_t stride, int64_t pad) {
+                           int64_t KH, int64_t KW, int64_t stride, int64_t pad, bool compact) {
   using namespace conv;
   check5(dy, "dy");
   check_arena(w_arena, dy.size(0));
   ConvP p = make_params(dy.size(0), dy.size(1), Cin, Hi, Wi, dy.size(2), KH, KW, stride, pad, w_arena.size(1));
+  p.compact = compact ? 1 : 0;
   TORCH_CHECK(p.Ho == dy.size(3) && p.Wo == dy.size(4), "dy spatial size mismatch");
   const c10::cuda::CUDAGuard guard(dy.device());
   const int M = p.B * p.Hi * p.Wi, K = p.Cout * p.ntaps;
@@ -722,13 +732,14 @@ at::Tensor slot_conv_dgrad(at::Tensor dy, at::Tensor w_arena, int64_t w_offset, 
 
 // accumulates into g_arena[s, g_offset : g_offset + Cout*Cin*KH*KW]  (the arena must be zero or hold a partial sum)
 void slot_conv_wgrad(at::Tensor x, at::Tensor dy, at::Tensor g_arena, int64_t g_offset, int64_t KH, int64_t KW,
-                     int64_t stride, int64_t pad) {
+                     int64_t stride, int64_t pad, bool compact) {
   using namespace conv;
   check5(x, "x");
   check5(dy, "dy");
   check_arena(g_arena, x.size(0));
   ConvP p = make_params(x.size(0), x.size(1), x.size(2), x.size(3), x.size(4), dy.size(2), KH, KW, stride, pad,
                         g_arena.size(1));
+  p.compact = compact ? 1 : 0;
   TORCH_CHECK(p.Ho == dy.size(3) && p.Wo == dy.size(4), "dy spatial size mismatch");
   const c10::cuda::CUDAGuard guard(x.device());
   const int M = p.B * p.Ho * p.Wo, K = p.Cin * p.ntaps;

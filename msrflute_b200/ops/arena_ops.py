@@ -134,6 +134,33 @@ def pseudo_grad(w_global, w_local, out, weight: Optional[torch.Tensor] = None, s
     out.copy_(pg if weight is None else pg * weight)
 
 
+def scatter_in(W: torch.Tensor, w_global: torch.Tensor, index_map: torch.Tensor):
+    """``W[s, j] = w_global[index_map[j]]`` for every slot row (0 where ``index_map[j] < 0``) — the round's
+    "broadcast" into compact slot arenas."""
+    if _ext.use_cuda_kernels(W):
+        _ext.load().slot_scatter_in(W, w_global, index_map)
+        _ext.count_launch(1)
+        return W
+    idx = index_map.long().clamp(min=0)
+    row = torch.where(index_map >= 0, w_global[idx], torch.zeros((), dtype=W.dtype, device=W.device))
+    W.copy_(row.view(1, -1).expand_as(W))
+    return W
+
+
+def accumulate_pseudo_grad_mapped(acc, w_global, w_local, weights, active, index_map):
+    """``acc[map[j]] += Σ_s weights[s]·active[s]·(w_global[map[j]] − w_local[s, j])`` (compact slot arenas)."""
+    if _ext.use_cuda_kernels(acc):
+        _ext.load().accumulate_pseudo_grad_mapped(acc, w_global, w_local, weights, active, index_map)
+        _ext.count_launch(1)
+        return acc
+    keep = index_map >= 0
+    idx = index_map[keep].long()
+    w = weights * (active.to(weights.dtype) if active is not None else 1.0)
+    delta = (w.view(-1, 1) * (w_global[idx].view(1, -1) - w_local[:, keep])).sum(dim=0)
+    acc[idx] += delta
+    return acc
+
+
 def accumulate_pseudo_grad(acc, w_global, w_local, weights, active: Optional[torch.Tensor] = None):
     """``acc += Σ_s weights[s]·(w_global − w_local[s])`` over the active rows, one pass, weights on device."""
     wl = _2d(w_local)

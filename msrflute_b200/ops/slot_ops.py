@@ -30,33 +30,43 @@ def _ensure_impl():
         set_conv_impl(os.environ.get("FLUTE_CONV_IMPL", "auto"))
 
 
+def live_taps(Hi, Wi, KH, KW, stride, pad):
+    """Filter taps (kh, kw) that touch real input for at least one output position — same rule and order as
+    ``set_taps`` in ``csrc/conv_kernels.cu``.  The others only ever multiply zero padding."""
+    Ho, Wo = (Hi + 2 * pad - KH) // stride + 1, (Wi + 2 * pad - KW) // stride + 1
+    rows = [kh for kh in range(KH) if any(0 <= oh * stride - pad + kh < Hi for oh in range(Ho))]
+    cols = [kw for kw in range(KW) if any(0 <= ow * stride - pad + kw < Wi for ow in range(Wo))]
+    return [(kh, kw) for kh in rows for kw in cols]
+
+
 class SlotConv2d(torch.autograd.Function):
-    """x [S, B, Cin, H, W] (fp32) * per-slot weight [Cout, Cin, KH, KW] at W[s, w_off:] → [S, B, Cout, Ho, Wo]."""
+    """x [S, B, Cin, H, W] (fp32) * per-slot weight [Cout, Cin, KH, KW] at W[s, w_off:] → [S, B, Cout, Ho, Wo].
+    ``compact``: the slot arena stores only the live taps of this filter, ``[Cout, Cin, len(live_taps)]``."""
 
     @staticmethod
-    def forward(ctx, x, dummy, W, G, w_off, Cout, KH, KW, stride, pad):
+    def forward(ctx, x, dummy, W, G, w_off, Cout, KH, KW, stride, pad, compact=False):
         ext = _ext.load()
         _ensure_impl()
         x = x.contiguous()
-        y = ext.slot_conv_fprop(x, W, w_off, Cout, KH, KW, stride, pad)
+        y = ext.slot_conv_fprop(x, W, w_off, Cout, KH, KW, stride, pad, bool(compact))
         _ext.count_launch(1)
         ctx.save_for_backward(x)
-        ctx.W, ctx.G, ctx.cfg = W, G, (w_off, KH, KW, stride, pad)
+        ctx.W, ctx.G, ctx.cfg = W, G, (w_off, KH, KW, stride, pad, bool(compact))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
-        w_off, KH, KW, stride, pad = ctx.cfg
+        w_off, KH, KW, stride, pad, compact = ctx.cfg
         ext = _ext.load()
         dy = dy.contiguous()
-        ext.slot_conv_wgrad(x, dy, ctx.G, w_off, KH, KW, stride, pad)             # accumulates into the grad arena
+        ext.slot_conv_wgrad(x, dy, ctx.G, w_off, KH, KW, stride, pad, compact)    # accumulates into the grad arena
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = ext.slot_conv_dgrad(dy, ctx.W, w_off, x.shape[2], x.shape[3], x.shape[4], KH, KW, stride, pad)
+            dx = ext.slot_conv_dgrad(dy, ctx.W, w_off, x.shape[2], x.shape[3], x.shape[4], KH, KW, stride, pad, compact)
             _ext.count_launch(1)
         _ext.count_launch(1)
-        return dx, None, None, None, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None, None, None, None
 
 
 class SlotGroupNorm(torch.autograd.Function):

@@ -120,3 +120,39 @@ def test_arena_layout_alignment_and_views():
     assert w.flat[:15].eq(2.0).all() and w.flat[15:32].eq(0).all()
     m(torch.randn(2, 5)).sum().backward()
     assert g.flat[:15].abs().sum() > 0
+
+
+def test_compact_slot_plan_and_mapped_ops_match_full_arena():
+    """Dead-tap elision: the compact slot layout + mapped broadcast/gather are equivalent to the full arenas."""
+    import torch
+    from msrflute_b200.models.resnet_gn import RESNET
+    from msrflute_b200.models.slot_resnet import SlotBatchedResNet
+    from msrflute_b200.ops import arena_ops
+    from msrflute_b200.ops.slot_ops import live_taps
+    from msrflute_b200.parallel.arena import ArenaLayout
+
+    assert live_taps(1, 1, 3, 3, 1, 1) == [(1, 1)]
+    assert live_taps(2, 2, 3, 3, 2, 1) == [(1, 1), (1, 2), (2, 1), (2, 2)]
+    assert len(live_taps(8, 8, 3, 3, 1, 1)) == 9
+    torch.manual_seed(0)
+    model = RESNET({"group_norm": 2, "num_classes": 10})
+    lay = ArenaLayout.from_module(model)
+    plan = SlotBatchedResNet.plan_compact(model, lay, torch.zeros(2, 3, 32, 32))
+    assert plan is not None and plan["numel"] < 0.45 * lay.numel            # layer4's 3x3 filters keep 1 tap of 9
+    assert any("layer4" in n for n in plan["compact"]) and not any("layer1" in n for n in plan["compact"])
+    m = plan["index_map"]
+    live = m[m >= 0].long()
+    assert live.unique().numel() == live.numel() and int(live.max()) < lay.padded_numel
+    S, P = 3, lay.padded_numel
+    wg = torch.randn(P)
+    W = torch.zeros(S, plan["numel"])
+    arena_ops.scatter_in(W, wg, m)
+    assert torch.equal(W[1][m >= 0], wg[live]) and float(W[:, m < 0].abs().sum()) == 0
+    W += torch.randn_like(W) * (m >= 0)
+    Wfull = wg.view(1, -1).repeat(S, 1)
+    Wfull[:, live] = W[:, m >= 0]
+    wts, act = torch.tensor([1.0, 2.0, 3.0]), torch.tensor([1, 0, 1], dtype=torch.int32)
+    acc_c, acc_f = torch.zeros(P), torch.zeros(P)
+    arena_ops.accumulate_pseudo_grad_mapped(acc_c, wg, W, wts, act, m)
+    arena_ops.accumulate_pseudo_grad(acc_f, wg, Wfull, wts, act)
+    assert torch.allclose(acc_c, acc_f, atol=1e-5)

@@ -487,3 +487,45 @@ def test_cosine_stats_kernel():
     from msrflute_b200.utils import compute_grad_cosines
     cs = compute_grad_cosines([[a[:100], a[100:]], [b]], [a])
     assert abs(cs[0] - 1.0) < 1e-5 and abs(cs[1] - (ref[0] / (ref[1] * ref[2]).sqrt()).item()) < 1e-4
+
+
+@pytest.mark.parametrize("cfg", [(2, 20, 512, 1, 512, 3, 1, 1), (3, 20, 256, 2, 512, 3, 2, 1), (2, 20, 64, 1, 96, 5, 1, 2)])
+@pytest.mark.parametrize("impl", ["fma", "tcgen05"])
+def test_slot_conv_compact_weights_match_full_layout(cfg, impl):
+    """Compact slot arenas store only the live taps of a filter ([Cout, Cin, ntaps]); outputs and input gradients must
+    equal the full-layout run and the weight gradient must equal the live taps of the full-layout gradient."""
+    ext = _ext()
+    from msrflute_b200.ops.slot_ops import SlotConv2d, live_taps
+    S, B, Cin, H, Cout, k, stride, pad = cfg
+    taps = live_taps(H, H, k, k, stride, pad)
+    assert len(taps) < k * k
+    torch.manual_seed(21)
+    ext.slot_conv_set_impl(1 if impl == "fma" else 2)
+    try:
+        n_full, n_c = Cout * Cin * k * k, Cout * Cin * len(taps)
+        off = 64
+        Wf = torch.zeros(S, off + n_full + 32, device="cuda")
+        Wf[:, off:off + n_full] = torch.randn(S, n_full, device="cuda") * 0.1
+        tap_idx = torch.tensor([kh * k + kw for kh, kw in taps], device="cuda")
+        Wc = torch.zeros(S, off + n_c + 32, device="cuda")
+        Wc[:, off:off + n_c] = Wf[:, off:off + n_full].view(S, Cout * Cin, k * k)[:, :, tap_idx].reshape(S, -1)
+        Gf, Gc = torch.zeros_like(Wf), torch.zeros_like(Wc)
+        x = torch.randn(S, B, Cin, H, H, device="cuda")
+        dummy = torch.zeros(1, device="cuda", requires_grad=True)
+        outs = []
+        for W, G, compact in ((Wf, Gf, False), (Wc, Gc, True)):
+            xi = x.clone().requires_grad_(True)
+            y = SlotConv2d.apply(xi, dummy, W, G, off, Cout, k, k, stride, pad, compact)
+            torch.manual_seed(22)
+            y.backward(torch.randn_like(y))
+            outs.append((y.detach(), xi.grad))
+        tol = dict(atol=1e-4, rtol=1e-4) if impl == "fma" else dict(atol=2e-2, rtol=2e-2)
+        assert torch.allclose(outs[0][0], outs[1][0], **tol) and torch.allclose(outs[0][1], outs[1][1], **tol)
+        gf = Gf[:, off:off + n_full].view(S, Cout * Cin, k * k)
+        assert torch.allclose(gf[:, :, tap_idx].reshape(S, -1), Gc[:, off:off + n_c], **tol)
+        dead = torch.ones(k * k, dtype=torch.bool, device="cuda")
+        dead[tap_idx] = False
+        assert float(gf[:, :, dead].abs().sum()) == 0                  # dead taps really have zero gradient
+        assert float(Gc[:, :off].abs().sum()) == 0 and float(Gc[:, off + n_c:].abs().sum()) == 0
+    finally:
+        ext.slot_conv_set_impl(0)

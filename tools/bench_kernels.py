@@ -93,16 +93,16 @@ def bench_conv(out):
         W = torch.randn(S, P, device="cuda") * 0.05
         G = torch.zeros(S, P, device="cuda")
         x = torch.randn(S, B, Cin, H, H, device="cuda")
-        y = ext.slot_conv_fprop(x, W, 0, Cout, k, k, stride, pad)
+        y = ext.slot_conv_fprop(x, W, 0, Cout, k, k, stride, pad, False)
         dy = torch.randn_like(y)
         ext.slot_conv_set_impl(1)
-        f, _ = timeit(lambda: ext.slot_conv_fprop(x, W, 0, Cout, k, k, stride, pad))
-        d, _ = timeit(lambda: ext.slot_conv_dgrad(dy, W, 0, Cin, H, H, k, k, stride, pad))
-        wg, _ = timeit(lambda: ext.slot_conv_wgrad(x, dy, G, 0, k, k, stride, pad))
+        f, _ = timeit(lambda: ext.slot_conv_fprop(x, W, 0, Cout, k, k, stride, pad, False))
+        d, _ = timeit(lambda: ext.slot_conv_dgrad(dy, W, 0, Cin, H, H, k, k, stride, pad, False))
+        wg, _ = timeit(lambda: ext.slot_conv_wgrad(x, dy, G, 0, k, k, stride, pad, False))
         ext.slot_conv_set_impl(2)
-        tf, _ = timeit(lambda: ext.slot_conv_fprop(x, W, 0, Cout, k, k, stride, pad))
-        td, _ = timeit(lambda: ext.slot_conv_dgrad(dy, W, 0, Cin, H, H, k, k, stride, pad))
-        tw, _ = timeit(lambda: ext.slot_conv_wgrad(x, dy, G, 0, k, k, stride, pad))
+        tf, _ = timeit(lambda: ext.slot_conv_fprop(x, W, 0, Cout, k, k, stride, pad, False))
+        td, _ = timeit(lambda: ext.slot_conv_dgrad(dy, W, 0, Cin, H, H, k, k, stride, pad, False))
+        tw, _ = timeit(lambda: ext.slot_conv_wgrad(x, dy, G, 0, k, k, stride, pad, False))
         ext.slot_conv_set_impl(0)
         fl = 2.0 * S * B * y.shape[3] * y.shape[4] * Cout * Cin * k * k
         torch.backends.cudnn.allow_tf32 = True
