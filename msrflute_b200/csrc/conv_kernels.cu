@@ -24,6 +24,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/types.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -667,7 +668,15 @@ static void launch_tc(const float* in0, const float* in1, float* out, const Conv
 
 // 0 = auto (tcgen05 when the GEMM has >= 48 rows / reduction items per slot), 1 = FMA kernels only, 2 = tcgen05 always
 static int g_conv_impl = 0;
-static bool use_tc(int work_rows) { return g_conv_impl == 2 || (g_conv_impl == 0 && work_rows >= 48); }
+static int tc_min_rows() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("FLUTE_CONV_TC_MIN_ROWS");
+    v = e != nullptr ? std::max(1, std::atoi(e)) : 48;
+  }
+  return v;
+}
+static bool use_tc(int work_rows) { return g_conv_impl == 2 || (g_conv_impl == 0 && work_rows >= tc_min_rows()); }
 
 }  // namespace conv
 
