@@ -47,6 +47,7 @@ at::Tensor slot_conv_dgrad(at::Tensor dy, at::Tensor w_arena, int64_t w_offset, 
 void slot_conv_wgrad(at::Tensor x, at::Tensor dy, at::Tensor g_arena, int64_t g_offset, int64_t KH, int64_t KW,
                      int64_t stride, int64_t pad, bool compact);
 void slot_conv_set_impl(int64_t impl);
+void gemm_set_impl(int64_t impl);
 void slot_scatter_in(torch::Tensor W, torch::Tensor wg, torch::Tensor map);
 void accumulate_pseudo_grad_mapped(torch::Tensor acc, torch::Tensor wg, torch::Tensor wl, torch::Tensor weights,
                                    c10::optional<torch::Tensor> active, torch::Tensor map);
@@ -77,6 +78,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("slot_conv_dgrad", &flute::slot_conv_dgrad);
   m.def("slot_conv_wgrad", &flute::slot_conv_wgrad);
   m.def("slot_conv_set_impl", &flute::slot_conv_set_impl);
+  m.def("gemm_set_impl", &flute::gemm_set_impl);
   m.def("slot_scatter_in", &flute::slot_scatter_in);
   m.def("accumulate_pseudo_grad_mapped", &flute::accumulate_pseudo_grad_mapped);
   m.def("seg_minmax", &flute::seg_minmax);

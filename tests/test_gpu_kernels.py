@@ -224,7 +224,17 @@ def test_flagship_rounds_reduce_loss():
 @pytest.mark.parametrize("G,M,N,K", [(1, 128, 64, 64), (1, 20, 1000, 512), (1, 1280, 64, 576), (1, 320, 90, 256),
                                      (3, 200, 130, 200), (1, 4096, 4096, 1024), (10, 80, 256, 2304)])
 @pytest.mark.parametrize("epi", [(False, False, True), (True, True, False)])
-def test_gemm_tcgen05_matches_fp32_reference(G, M, N, K, epi):
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])      # auto | one tile per CTA | persistent BLOCK_N 128 | persistent 256
+def test_gemm_tcgen05_matches_fp32_reference(G, M, N, K, epi, impl):
+    ext = _ext()
+    ext.gemm_set_impl(impl)
+    try:
+        _gemm_check(G, M, N, K, epi)
+    finally:
+        ext.gemm_set_impl(0)
+
+
+def _gemm_check(G, M, N, K, epi):
     ext = _ext()
     if not hasattr(ext, "gemm_bf16_tn"):
         pytest.skip("GEMM not built")

@@ -42,11 +42,17 @@ def bench_gemm(out):
                       (1280, 64, 576), (20, 1000, 512)]:
         a = torch.randn(M, K, device="cuda").bfloat16()
         b = torch.randn(N, K, device="cuda").bfloat16()
-        ours, _ = timeit(lambda: ext.gemm_bf16_tn(a, b, None, False, False))
+        per_impl = {}
+        for name, impl in (("simple", 1), ("persistent128", 2), ("persistent256", 3), ("auto", 0)):
+            ext.gemm_set_impl(impl)
+            per_impl[name], _ = timeit(lambda: ext.gemm_bf16_tn(a, b, None, False, False))
+        ext.gemm_set_impl(0)
+        ours = per_impl["auto"]
         lib, _ = timeit(lambda: torch.matmul(a, b.t()))
         fl = 2.0 * M * N * K
         rows.append({"M": M, "N": N, "K": K, "ours_ms": ours, "cublas_ms": lib, "ours_tflops": fl / ours / 1e9,
-                     "cublas_tflops": fl / lib / 1e9, "frac_of_measured_peak": fl / ours / 1e9 / PEAKS["bf16_tflops"]})
+                     "cublas_tflops": fl / lib / 1e9, "frac_of_measured_peak": fl / ours / 1e9 / PEAKS["bf16_tflops"],
+                     "tflops_by_impl": {k: fl / v / 1e9 for k, v in per_impl.items()}})
         print(rows[-1])
     out["gemm_tcgen05"] = rows
 
