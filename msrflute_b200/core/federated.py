@@ -125,9 +125,16 @@ def get_comm() -> Communicator:
     return _Runtime.comm
 
 
-def assign_clients(items: List[int], costs: List[float], workers: List[int], policy: str = "static_lpt"):
-    """Split ``items`` over ``workers``.  ``static_lpt``: sort by cost descending, always give the next item
-    to the least-loaded worker (≤ 4/3 of the optimal makespan); ``round_robin``: i-th item → i mod W."""
+def assign_clients(items: List[int], costs: List[float], workers: List[int], policy: str = "static_lpt",
+                   speeds: Optional[dict] = None):
+    """Split ``items`` over ``workers``.
+
+    ``static_lpt``: sort by cost descending, always give the next item to the least-loaded worker (≤ 4/3 of the optimal
+    makespan); ``round_robin``: i-th item → i mod W; ``dynamic``: LPT on *estimated finish time* ``load / speed`` where
+    ``speeds[w]`` (cost units per second) is an exponential moving average of what each worker actually delivered in
+    earlier rounds (:func:`update_worker_speeds`).  The reference balances load by handing the next client to whichever
+    worker acknowledges first (``federated.py:282-410``); with one command per worker per round the same adaptation to
+    slow / shared / heterogeneous GPUs comes from the measured speeds instead of per-client round trips."""
     out = {w: [] for w in workers}
     if not workers:
         return out
@@ -135,12 +142,30 @@ def assign_clients(items: List[int], costs: List[float], workers: List[int], pol
         for i, it in enumerate(items):
             out[workers[i % len(workers)]].append(it)
         return out
+    speed = {w: 1.0 for w in workers}
+    if policy == "dynamic" and speeds:
+        known = [v for w, v in speeds.items() if w in speed and v > 0]
+        default = sum(known) / len(known) if known else 1.0
+        speed = {w: (speeds.get(w) if speeds.get(w, 0) > 0 else default) for w in workers}
     load = {w: 0.0 for w in workers}
     for it, c in sorted(zip(items, costs), key=lambda x: -x[1]):
-        w = min(workers, key=lambda k: (load[k], k))
+        c = max(float(c), 1e-9)
+        w = min(workers, key=lambda k: ((load[k] + c) / speed[k], k))
         out[w].append(it)
-        load[w] += max(float(c), 1e-9)
+        load[w] += c
     return out
+
+
+def update_worker_speeds(assign, costs_by_item, seconds_by_worker, momentum=0.7):
+    """EMA of cost units per second per worker from one round's measurements (``dynamic`` dispatch)."""
+    speeds = _Runtime.options.setdefault("_worker_speeds", {})
+    for w, items in assign.items():
+        t = seconds_by_worker.get(w, 0.0)
+        if not items or t <= 0:
+            continue
+        v = sum(max(float(costs_by_item.get(i, 1.0)), 1e-9) for i in items) / t
+        speeds[w] = v if w not in speeds else momentum * speeds[w] + (1 - momentum) * v
+    return speeds
 
 
 class Server:
@@ -173,7 +198,9 @@ class Server:
         workers = Server._workers(comm)
         costs = costs if costs is not None else [1.0] * len(clients)
         policy = _Runtime.options.get("dispatch", "static_lpt")
-        assign = assign_clients(list(clients), list(costs), workers, policy)
+        assign = assign_clients(list(clients), list(costs), workers, policy,
+                                speeds=_Runtime.options.get("_worker_speeds"))
+        cost_of = dict(zip(clients, costs))
         flat_ok = torch.is_tensor(weights)
         ctrl = {"cmd": command, "lr": lr, "round": nround, "assign": assign, "mode": mode, "fused": fused,
                 "sync": ("flat" if flat_ok else "list" if weights is not None else "none") if sync_weights else "none",
@@ -199,7 +226,8 @@ class Server:
         if ctrl["defer"] and comm.size > 1:
             # multi-rank deferred round: the cross-rank reduction of the accumulators and of Σ weight is enqueued
             # right behind the local training; per-client records are gathered (host, gloo) only on resolve()
-            yield _finish_deferred(comm, worker, local_out, len(clients))
+            yield _finish_deferred(comm, worker, local_out, len(clients), assign=assign,
+                                   cost_of=cost_of if policy == "dynamic" else None)
             return
         for o in local_out:
             yield o
@@ -210,6 +238,9 @@ class Server:
                 records = comm.gather_objects([_strip(o) for o in local_out])
                 if fused:
                     comm.reduce_accumulators(worker.accumulator(), dst=0)
+                if policy == "dynamic":
+                    update_worker_speeds(assign, cost_of, {r: sum(float(o["cs"].get("training", 0.0)) for o in recs)
+                                                          for r, recs in enumerate(records)})
                 for r, recs in enumerate(records):
                     if r == comm.rank:
                         continue
@@ -274,7 +305,7 @@ class Server:
             comm.bcast_object({"cmd": COMMAND_TERMINATE}, src=0)
 
 
-def _finish_deferred(comm, worker, local, n_clients):
+def _finish_deferred(comm, worker, local, n_clients, assign=None, cost_of=None):
     """Every rank calls this with its (possibly deferred / empty) local result, in the same order: NCCL/symm reduce of
     the accumulators → all-reduce of Σ weight → (on resolve) host sync + gloo gather of the per-client records."""
     from .engine import DeferredRound
@@ -297,6 +328,9 @@ def _finish_deferred(comm, worker, local, n_clients):
         for r, recs in enumerate(records):
             if r != comm.rank:
                 merged.extend(recs)
+        if cost_of is not None:                                     # ``dynamic`` dispatch: learn the workers' speeds
+            update_worker_speeds(assign, cost_of, {r: sum(float(o["cs"].get("training", 0.0)) for o in recs)
+                                                  for r, recs in enumerate(records)})
         return merged
 
     return DeferredRound(n_clients, wsum[0], resolve)

@@ -153,3 +153,19 @@ def test_fedlabels_average_of_sup_and_weighted_unsup():
     for p in model.parameters():
         assert torch.allclose(p.data, torch.full_like(p, (sup_avg + unsup_avg) / 2))
     assert set(srv.tmp_sup.keys()) == set(keys)
+
+
+def test_dispatch_policies_lpt_round_robin_dynamic():
+    from msrflute_b200.core import federated as F
+    items, costs = list(range(8)), [8, 7, 6, 5, 4, 3, 2, 1]
+    rr = F.assign_clients(items, costs, [0, 1], "round_robin")
+    assert rr == {0: [0, 2, 4, 6], 1: [1, 3, 5, 7]}
+    lpt = F.assign_clients(items, costs, [0, 1], "static_lpt")
+    assert abs(sum(costs[i] for i in lpt[0]) - sum(costs[i] for i in lpt[1])) <= 1
+    # dynamic: a worker measured 3x slower gets ~1/4 of the work
+    F._Runtime.options.pop("_worker_speeds", None)
+    F.update_worker_speeds({0: [0, 1], 1: [2, 3]}, {0: 10, 1: 10, 2: 10, 3: 10}, {0: 1.0, 1: 3.0})
+    dyn = F.assign_clients(items, costs, [0, 1], "dynamic", speeds=F._Runtime.options["_worker_speeds"])
+    load = {w: sum(costs[i] for i in v) for w, v in dyn.items()}
+    assert load[0] > 2.3 * load[1] and sorted(dyn[0] + dyn[1]) == items
+    F._Runtime.options.pop("_worker_speeds", None)
