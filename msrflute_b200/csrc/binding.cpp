@@ -48,6 +48,10 @@ void slot_conv_wgrad(at::Tensor x, at::Tensor dy, at::Tensor g_arena, int64_t g_
                      int64_t stride, int64_t pad, bool compact);
 void slot_conv_set_impl(int64_t impl);
 void gemm_set_impl(int64_t impl);
+std::vector<torch::Tensor> layer_norm_fwd(torch::Tensor x, c10::optional<torch::Tensor> weight, c10::optional<torch::Tensor> bias,
+                                          double eps);
+std::vector<torch::Tensor> layer_norm_bwd(torch::Tensor dy, torch::Tensor x, c10::optional<torch::Tensor> weight,
+                                          torch::Tensor mean, torch::Tensor rstd);
 void slot_scatter_in(torch::Tensor W, torch::Tensor wg, torch::Tensor map);
 void accumulate_pseudo_grad_mapped(torch::Tensor acc, torch::Tensor wg, torch::Tensor wl, torch::Tensor weights,
                                    c10::optional<torch::Tensor> active, torch::Tensor map);
@@ -79,6 +83,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("slot_conv_wgrad", &flute::slot_conv_wgrad);
   m.def("slot_conv_set_impl", &flute::slot_conv_set_impl);
   m.def("gemm_set_impl", &flute::gemm_set_impl);
+  m.def("layer_norm_fwd", &flute::layer_norm_fwd);
+  m.def("layer_norm_bwd", &flute::layer_norm_bwd);
   m.def("slot_scatter_in", &flute::slot_scatter_in);
   m.def("accumulate_pseudo_grad_mapped", &flute::accumulate_pseudo_grad_mapped);
   m.def("seg_minmax", &flute::seg_minmax);

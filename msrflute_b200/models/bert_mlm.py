@@ -91,6 +91,10 @@ class BERT(BaseModel):
             enc = getattr(self.model, "bert", None) or getattr(self.model, "roberta", None)
             if enc is not None:
                 self.tc_layers = swap_linear_modules(enc)
+        self.fused_layer_norms = 0
+        if model_args.get("fused_layer_norm", True):
+            from ..ops.norm_ops import swap_layer_norm_modules
+            self.fused_layer_norms = swap_layer_norm_modules(self.model)     # one fwd + one bwd kernel per LayerNorm
         n = sum(p.numel() for p in self.model.parameters())
         print_rank("mlm_bert: {} with {:.1f}M parameters".format(self.model_name, n / 1e6), logging.INFO)
 

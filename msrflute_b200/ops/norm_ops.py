@@ -147,3 +147,63 @@ def layer_norm(x, weight, bias, eps=1e-5, residual=None):
     if residual is not None:
         x = x + residual
     return F.layer_norm(x, (x.shape[-1],), weight, bias, eps)
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        ext = _ext.load()
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous()
+        w = weight.float().contiguous() if weight is not None else None
+        b = bias.float().contiguous() if bias is not None else None
+        y, mean, rstd = ext.layer_norm_fwd(x2, w, b, float(eps))
+        _ext.count_launch(1)
+        ctx.save_for_backward(x2, w, mean, rstd)
+        ctx.in_shape, ctx.affine = shp, weight is not None
+        ctx.w_dtype = weight.dtype if weight is not None else None
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, mean, rstd = ctx.saved_tensors
+        ext = _ext.load()
+        dx, dw, db = ext.layer_norm_bwd(dy.reshape(x2.shape).to(x2.dtype).contiguous(), x2, w, mean, rstd)
+        _ext.count_launch(1)
+        if not ctx.affine:
+            return dx.view(ctx.in_shape), None, None, None
+        return dx.view(ctx.in_shape), dw.to(ctx.w_dtype), db.to(ctx.w_dtype), None
+
+
+def layer_norm(x, weight=None, bias=None, eps: float = 1e-5):
+    """LayerNorm over the last dimension.  CUDA (fp32 / bf16): ``csrc/layernorm_kernels.cu`` — one warp per row, the
+    backward produces dx, dγ and dβ in one kernel.  Elsewhere: ``F.layer_norm``."""
+    if _ext.use_cuda_kernels(x) and x.dtype in (torch.float32, torch.bfloat16) and x.shape[-1] <= 6144 \
+            and (weight is None) == (bias is None):
+        return _LayerNormFn.apply(x, weight, bias, eps)
+    return F.layer_norm(x, (x.shape[-1],), weight, bias, eps)
+
+
+class FusedLayerNorm(torch.nn.LayerNorm):
+    """Drop-in ``nn.LayerNorm`` (1-D normalized_shape) running :func:`layer_norm`."""
+
+    def forward(self, x):
+        if len(self.normalized_shape) != 1:
+            return super().forward(x)
+        return layer_norm(x, self.weight, self.bias, self.eps)
+
+
+def swap_layer_norm_modules(module: torch.nn.Module) -> int:
+    """Replace every 1-D ``nn.LayerNorm`` by a :class:`FusedLayerNorm` sharing its parameters; returns the count."""
+    n = 0
+    for name, child in list(module.named_children()):
+        if type(child) is torch.nn.LayerNorm and len(child.normalized_shape) == 1:
+            new = FusedLayerNorm(child.normalized_shape, eps=child.eps, elementwise_affine=child.elementwise_affine,
+                                 device=child.weight.device if child.weight is not None else None)
+            new.weight, new.bias = child.weight, child.bias
+            setattr(module, name, new)
+            n += 1
+        else:
+            n += swap_layer_norm_modules(child)
+    return n

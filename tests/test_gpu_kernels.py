@@ -539,3 +539,34 @@ def test_slot_conv_compact_weights_match_full_layout(cfg, impl):
         assert float(Gc[:, :off].abs().sum()) == 0 and float(Gc[:, off + n_c:].abs().sum()) == 0
     finally:
         ext.slot_conv_set_impl(0)
+
+
+@pytest.mark.parametrize("shape,dtype,affine", [((64, 128, 768), torch.float32, True), ((5, 7, 100), torch.float32, True),
+                                                ((1000, 256), torch.bfloat16, True), ((33, 48), torch.float32, False)])
+def test_layer_norm_kernel_matches_torch(shape, dtype, affine):
+    _ext()
+    from msrflute_b200.ops import norm_ops
+    torch.manual_seed(31)
+    H = shape[-1]
+    x = (torch.randn(shape, device="cuda") * 2 + 0.3).to(dtype).requires_grad_(True)
+    w = (torch.rand(H, device="cuda") + 0.5).requires_grad_(True) if affine else None
+    b = torch.randn(H, device="cuda").requires_grad_(True) if affine else None
+    y = norm_ops.layer_norm(x, w, b, 1e-5)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    x2 = x.detach().float().requires_grad_(True)
+    w2 = w.detach().clone().requires_grad_(True) if affine else None
+    b2 = b.detach().clone().requires_grad_(True) if affine else None
+    y2 = torch.nn.functional.layer_norm(x2, (H,), w2, b2, 1e-5)
+    y2.backward(dy.float())
+    tol = dict(atol=2e-4, rtol=2e-4) if dtype == torch.float32 else dict(atol=6e-2, rtol=6e-2)
+    assert torch.allclose(y.float(), y2, **tol), (y.float() - y2).abs().max()
+    assert torch.allclose(x.grad.float(), x2.grad, **tol), (x.grad.float() - x2.grad).abs().max()
+    if affine:
+        rows = x.numel() // H
+        assert torch.allclose(w.grad, w2.grad, atol=tol["atol"] * rows ** 0.5, rtol=tol["rtol"] * 5)
+        assert torch.allclose(b.grad, b2.grad, atol=tol["atol"] * rows ** 0.5, rtol=tol["rtol"] * 5)
+    m = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.LayerNorm(32)).cuda()
+    assert norm_ops.swap_layer_norm_modules(m) == 1 and isinstance(m[1], norm_ops.FusedLayerNorm)
+    assert torch.allclose(m(torch.ones(2, 16, device="cuda")), torch.nn.functional.layer_norm(
+        m[0](torch.ones(2, 16, device="cuda")), (32,), m[1].weight, m[1].bias), atol=1e-5)
