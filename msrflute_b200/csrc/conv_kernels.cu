@@ -38,6 +38,15 @@ struct ConvP {
   int splits;                 // reduction splits (blockIdx.z = slot * splits + split)
   int ntaps;                  // taps that touch real data for at least one output position
   int compact;                // 1: the weight tensor stores ONLY the live taps, [Cout, Cin, ntaps] (compact slot arenas)
+  // tcgen05 dgrad of a stride-2 convolution is split into its 4 parity classes (ih+pad, iw+pad mod 2): an input pixel of
+  // class (ph, pw) only receives taps with kh = ph, kw = pw (mod 2), so each class is a dense stride-1-like problem with
+  // ~1/4 of the taps instead of a 4x larger masked one.  cls = ph * 2 + pw.
+  int ncls;                       // 0 = no decomposition, 4 = by parity
+  int cls_tile0[5];               // first row-tile (blockIdx.x) of each class, [4] = total
+  int cls_h0[2], cls_hc[2];       // first ih of parity ph and how many rows have it
+  int cls_w0[2], cls_wc[2];
+  unsigned char cls_ntaps[4];
+  unsigned char cls_tap_idx[4][16];   // indices into taps[]
   long long w_slot_stride;    // floats between two slots' copies of this weight tensor (= arena row length P)
   unsigned short taps[MAX_TAPS];   // kh << 8 | kw
 };
@@ -339,6 +348,7 @@ static ConvP make_params(int64_t S, int64_t B, int64_t Cin, int64_t Hi, int64_t 
   p.w_slot_stride = w_slot_stride;
   p.splits = 1;
   p.compact = 0;
+  p.ncls = 0;
   set_taps(p);
   return p;
 }
@@ -376,7 +386,7 @@ using namespace tc;
 constexpr int TM = 128, TN = 64, TK = 32, T_UMMA_K = 8, T_STAGES = 4;
 constexpr int T_PRODUCERS = 256, T_THREADS = 288;
 constexpr int T_A_BYTES = TM * TK * 4, T_B_BYTES = TN * TK * 4, T_STAGE_BYTES = T_A_BYTES + T_B_BYTES;
-constexpr int T_TABLE_BYTES = TM * 8 + 64 * 8;             // wgrad row table + per-tap (offset, dh, dw) table
+constexpr int T_TABLE_BYTES = TM * 8 + 64 * 8 + 64 * 4;    // wgrad row table + per-tap (offset, kh, kw) table + tap ids
 constexpr int T_SMEM = T_STAGES * T_STAGE_BYTES + T_TABLE_BYTES + 256 + 1024;
 enum { FPROP = 0, DGRAD = 1, WGRAD = 2 };
 
@@ -393,6 +403,7 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   int2* row_table = reinterpret_cast<int2*>(smem + T_STAGES * T_STAGE_BYTES);
   int2* tap_table = row_table + TM;                  // [ntaps] {kh * W + kw, kh << 16 | kw}: no LDC / branches in the gathers
+  int* tap_gidx = reinterpret_cast<int*>(tap_table + 64);   // index of the tap in p.taps[] (weight addressing)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T_STAGES * T_STAGE_BYTES + T_TABLE_BYTES);
   uint64_t* empty_bar = full_bar + T_STAGES;
   uint64_t* acc_bar = empty_bar + T_STAGES;
@@ -402,10 +413,21 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
   const int slot = blockIdx.z / p.splits, split = blockIdx.z - slot * p.splits;
   const int KHW = p.KH * p.KW, HiWi = p.Hi * p.Wi, HoWo = p.Ho * p.Wo;
   // GEMM view of this mode: R rows x C cols, reduction length RED
-  const int R = MODE == FPROP ? p.B * HoWo : MODE == DGRAD ? p.B * HiWi : p.Cin * p.ntaps;
+  // parity class of this CTA (stride-2 dgrad only): its own row space, tap list and reduction length
+  int cls = -1, NT = p.ntaps, cls_h0 = 0, cls_w0 = 0, cls_hc = p.Hi, cls_wc = p.Wi, tile_x = blockIdx.x;
+  if (MODE == DGRAD && p.ncls == 4) {
+    cls = 0;
+    while (cls < 3 && tile_x >= p.cls_tile0[cls + 1]) ++cls;
+    tile_x -= p.cls_tile0[cls];
+    NT = p.cls_ntaps[cls];
+    cls_h0 = p.cls_h0[cls >> 1]; cls_hc = p.cls_hc[cls >> 1];
+    cls_w0 = p.cls_w0[cls & 1]; cls_wc = p.cls_wc[cls & 1];
+  }
+  const int pix_step = cls >= 0 ? 2 : 1;                                 // spacing of this CTA's pixels in the image
+  const int R = MODE == FPROP ? p.B * HoWo : MODE == DGRAD ? p.B * cls_hc * cls_wc : p.Cin * p.ntaps;
   const int C = MODE == FPROP ? p.Cout : MODE == DGRAD ? p.Cin : p.Cout;
-  const int RED = MODE == FPROP ? p.Cin * p.ntaps : MODE == DGRAD ? p.Cout * p.ntaps : p.B * HoWo;
-  const int r_tile0 = blockIdx.x * TM, c_tile0 = blockIdx.y * TN;
+  const int RED = MODE == FPROP ? p.Cin * p.ntaps : MODE == DGRAD ? p.Cout * NT : p.B * HoWo;
+  const int r_tile0 = tile_x * TM, c_tile0 = blockIdx.y * TN;
   const int stages_total = (RED + TK - 1) / TK;
   const int per = (stages_total + p.splits - 1) / p.splits;
   const int st_begin = split * per, st_end = min(stages_total, st_begin + per);
@@ -420,13 +442,15 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(tmem_ptr, TN);
-  if (tid >= TM && tid < TM + p.ntaps) {
+  if (tid >= TM && tid < TM + NT) {
     // .x = the tap's separable address offset: fprop  x[.., oh*s-pad+kh, ow*s-pad+kw]      -> + kh*Wi + kw
     //                                          dgrad dy[.., (ih+pad-kh)/s, (iw+pad-kw)/s]   -> - (kh/s)*Wo - kw/s
     //      (when s divides ih+pad-kh the quotient is floor((ih+pad)/s) - floor(kh/s));  .y = kh << 16 | kw
-    const int t = p.taps[tid - TM], kh = t >> 8, kw = t & 255;
+    const int gi = cls >= 0 ? p.cls_tap_idx[cls][tid - TM] : tid - TM;
+    const int t = p.taps[gi], kh = t >> 8, kw = t & 255;
     const int off = MODE == DGRAD ? -((kh / p.stride) * p.Wo + kw / p.stride) : kh * p.Wi + kw;
     tap_table[tid - TM] = make_int2(off, (kh << 16) | kw);
+    tap_gidx[tid - TM] = gi;
   }
   if (MODE == WGRAD && tid < TM) {                   // per-row (ci, tap) decode of this tile, shared by all stages
     const int k = r_tile0 + tid;
@@ -458,8 +482,10 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
     if (MODE == FPROP || MODE == DGRAD) {
       const int m = r_tile0 + row;
       if (m < R) {
-        const int HW = MODE == FPROP ? HoWo : HiWi, Wd = MODE == FPROP ? p.Wo : p.Wi;
-        const int b = m / HW, r = m - b * HW, ph = r / Wd, pw = r - ph * Wd;
+        const int HW = MODE == FPROP ? HoWo : cls_hc * cls_wc, Wd = MODE == FPROP ? p.Wo : cls_wc;
+        const int b = m / HW, r = m - b * HW;
+        int ph = r / Wd, pw = r - ph * Wd;
+        if (MODE == DGRAD) { ph = cls_h0 + ph * pix_step; pw = cls_w0 + pw * pix_step; }   // pixel of this class
         if (MODE == FPROP) {
           const int h0 = ph * p.stride - p.pad, w0 = pw * p.stride - p.pad;
           base = b * p.Cin * HiWi + h0 * p.Wi + w0;
@@ -472,7 +498,7 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
         } else {
           const int h0 = ph + p.pad, w0 = pw + p.pad;
           base = b * p.Cout * HoWo + (h0 / p.stride) * p.Wo + w0 / p.stride;
-          for (int t = 0; t < p.ntaps; ++t) {
+          for (int t = 0; t < NT; ++t) {
             const int2 tp = tap_table[t];
             const int th = h0 - (tp.y >> 16), tw = w0 - (tp.y & 0xFFFF);          // = oh * stride, ow * stride
             if (th >= 0 && tw >= 0 && th % p.stride == 0 && tw % p.stride == 0 && th / p.stride < p.Ho && tw / p.stride < p.Wo)
@@ -491,9 +517,9 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
         // ---- A: row gather, 16 reduction indices (channel, tap) of this thread's pixel.  Branch-free: masked
         // elements load element 0 and are zeroed by a select, so all 16 loads are in flight together.
         const int k = r0 + khalf * 16;
-        const int c0 = k / p.ntaps;                         // ci (fprop) / co (dgrad) of the first index
+        const int c0 = k / NT;                              // ci (fprop) / co (dgrad) of the first index
         const int CS = MODE == FPROP ? HiWi : HoWo;         // channel stride of the gathered tensor
-        int ti = k - c0 * p.ntaps;
+        int ti = k - c0 * NT;
         int cbase = base + c0 * CS;
         const int nvalid = RED - k;                         // reduction indices left (only the last stage is partial)
         float v[16];
@@ -502,7 +528,7 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
           const bool ok = ((tap_ok >> ti) & 1ull) != 0ull && j < nvalid;
           const float xv = __ldg(a_src + (ok ? cbase + tap_table[ti].x : 0));
           v[j] = ok ? xv : 0.f;
-          const bool wrap = ++ti == p.ntaps;
+          const bool wrap = ++ti == NT;
           ti = wrap ? 0 : ti;
           cbase += wrap ? CS : 0;
         }
@@ -524,10 +550,10 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
           const int kb = r0 + lane;
           long long woff = -1;
           if (kb < RED) {
-            const int cc = kb / p.ntaps, tib = kb - cc * p.ntaps;
+            const int cc = kb / NT, tib = kb - cc * NT;
             const int2 tp = tap_table[tib];
             const int wtaps = p.compact ? p.ntaps : KHW;                    // taps stored per (co, ci)
-            const int tap_off = p.compact ? tib : (tp.y >> 16) * p.KW + (tp.y & 0xFFFF);
+            const int tap_off = p.compact ? tap_gidx[tib] : (tp.y >> 16) * p.KW + (tp.y & 0xFFFF);
             woff = MODE == FPROP ? static_cast<long long>(cc) * wtaps + tap_off
                                  : static_cast<long long>(cc) * p.Cin * wtaps + tap_off;
           }
@@ -592,8 +618,14 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
             if (co < C) atomicAdd(dst + co * pitch, __uint_as_float(v[j]));
           }
         } else {
-          const int HW = MODE == FPROP ? HoWo : HiWi;
-          const int b = rr / HW, r = rr - b * HW;
+          const int HWr = MODE == FPROP ? HoWo : cls_hc * cls_wc;     // rows per image in this CTA's row space
+          const int HW = MODE == FPROP ? HoWo : HiWi;                 // pixels per channel plane of the output
+          const int b = rr / HWr;
+          int r = rr - b * HWr;
+          if (MODE == DGRAD && cls >= 0) {
+            const int jh = r / cls_wc, jw = r - jh * cls_wc;
+            r = (cls_h0 + 2 * jh) * p.Wi + cls_w0 + 2 * jw;
+          }
           float* dst = out + (static_cast<long long>(slot) * p.B + b) * C * HW + r;
           const int n_base = c_tile0 + chalf * 32;
           dst += static_cast<long long>(n_base) * HW;
@@ -653,13 +685,14 @@ static int pick_splits_tc(long long tiles, int stages) {
 }
 
 template <int MODE>
-static void launch_tc(const float* in0, const float* in1, float* out, const ConvP& p, int rows, int cols, int vec_b) {
+static void launch_tc(const float* in0, const float* in1, float* out, const ConvP& p, int rows, int cols, int vec_b,
+                      int row_tiles = -1) {
   static bool configured = false;
   if (!configured) {
     FLUTE_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
     configured = true;
   }
-  dim3 grid((rows + TM - 1) / TM, (cols + TN - 1) / TN, p.S * p.splits);
+  dim3 grid(row_tiles >= 0 ? row_tiles : (rows + TM - 1) / TM, (cols + TN - 1) / TN, p.S * p.splits);
   conv_tc_kernel<MODE><<<grid, T_THREADS, T_SMEM, at::cuda::getCurrentCUDAStream()>>>(in0, in1, out, p, vec_b);
   FLUTE_CUDA_CHECK(cudaGetLastError());
 }
@@ -721,7 +754,37 @@ at::Tensor slot_conv_dgrad(at::Tensor dy, at::Tensor w_arena, int64_t w_offset, 
   const c10::cuda::CUDAGuard guard(dy.device());
   const int M = p.B * p.Hi * p.Wi, K = p.Cout * p.ntaps;
   if (use_tc(M)) {
-    const long long tiles = static_cast<long long>((M + tcv::TM - 1) / tcv::TM) * ((p.Cin + tcv::TN - 1) / tcv::TN) * p.S;
+    const int n_tiles = (p.Cin + tcv::TN - 1) / tcv::TN;
+    if (p.stride == 2) {
+      // parity decomposition (see ConvP): 4 dense sub-problems instead of one 4x larger masked one
+      p.ncls = 4;
+      for (int par = 0; par < 2; ++par) {
+        const int h0 = ((par - p.pad) % 2 + 2) % 2, w0 = h0;
+        p.cls_h0[par] = h0; p.cls_hc[par] = h0 < p.Hi ? (p.Hi - h0 + 1) / 2 : 0;
+        p.cls_w0[par] = w0; p.cls_wc[par] = w0 < p.Wi ? (p.Wi - w0 + 1) / 2 : 0;
+      }
+      int tile0 = 0, max_taps = 0;
+      for (int c = 0; c < 4; ++c) {
+        const int ph = c >> 1, pw = c & 1;
+        int nt = 0;
+        for (int t = 0; t < p.ntaps; ++t)
+          if (((p.taps[t] >> 8) & 1) == ph && ((p.taps[t] & 255) & 1) == pw && nt < 16) p.cls_tap_idx[c][nt++] = static_cast<unsigned char>(t);
+        p.cls_ntaps[c] = static_cast<unsigned char>(nt);
+        max_taps = std::max(max_taps, nt);
+        p.cls_tile0[c] = tile0;
+        const int rows_c = p.B * p.cls_hc[ph] * p.cls_wc[pw];
+        if (nt > 0) tile0 += (rows_c + tcv::TM - 1) / tcv::TM;
+      }
+      p.cls_tile0[4] = tile0;
+      auto dx = at::zeros({p.S, p.B, p.Cin, p.Hi, p.Wi}, dy.options());     // classes without taps stay zero
+      if (tile0 > 0) {
+        p.splits = tcv::pick_splits_tc(static_cast<long long>(tile0) * n_tiles * p.S, (p.Cout * max_taps + tcv::TK - 1) / tcv::TK);
+        tcv::launch_tc<tcv::DGRAD>(dy.data_ptr<float>(), w_arena.data_ptr<float>() + w_offset, dx.data_ptr<float>(), p, M, p.Cin,
+                                   0, tile0);
+      }
+      return dx;
+    }
+    const long long tiles = static_cast<long long>((M + tcv::TM - 1) / tcv::TM) * n_tiles * p.S;
     p.splits = tcv::pick_splits_tc(tiles, (K + tcv::TK - 1) / tcv::TK);
     auto dx = p.splits > 1 ? at::zeros({p.S, p.B, p.Cin, p.Hi, p.Wi}, dy.options())
                            : at::empty({p.S, p.B, p.Cin, p.Hi, p.Wi}, dy.options());
