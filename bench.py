@@ -131,6 +131,10 @@ def main():
 
     server = job.server
     server.begin_training()
+    if comm.size > 1:
+        # setup, not warm-up: the first rounds of a multi-GPU job pay one-off costs (symmetric-memory peer mappings and
+        # signal pads, NCCL channel set-up, CUDA-graph capture on every rank) that take ~10 rounds to disappear
+        server.run_rounds(10)
     server.run_rounds(args.warmup)
     Server.sync_nodes()                                          # barrier + device synchronize on every rank
     sampler = ClockSampler(torch.cuda.current_device() if cuda else 0).start()
@@ -168,8 +172,10 @@ def main():
                        "all ranks stream their own shards)"}
     server.end_training()
     ms = max(dev_ms, 0.0)
+    rank_ms = None
     if comm.size > 1:
         others = [o for o in comm.gather_objects({"ms": ms}) if isinstance(o, dict)]
+        rank_ms = [round(float(o.get("ms", 0.0)), 3) for o in others]
         ms = max([ms] + [o.get("ms", 0.0) for o in others])
         if e2e is not None:
             e2e["h2d_bytes_per_step"] += sum(int(o.get("h2d", 0)) for o in others)
@@ -181,7 +187,7 @@ def main():
         "dtype": "bf16" if os.environ.get("FLUTE_BENCH_DTYPE", "fp32") == "bf16" else "fp32 (tf32 tensor-core convs)",
         "data": "synthetic Fed-CIFAR-100 shape (500 users x 100 x 32x32x3 uint8), random-init weights",
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "impl": "ours",
-        "last_train_loss": loss,
+        "last_train_loss": loss, "rank_ms": rank_ms if comm.size > 1 else None,
         "config": {"model": "ResNet-18 + {} (1000-way FC like the reference's RESNET), 11.7M params".format(
                        "GroupNorm(2 ch/group, per-group affine)" if args.norm == "gn" else "BatchNorm2d"),
                    "clients_per_round": args.clients_per_round, "client_batch": 20, "local_steps_per_client": 5,

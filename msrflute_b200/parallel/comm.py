@@ -175,7 +175,13 @@ def make_communicator(kind: str = "auto", device=None) -> Communicator:
         return LocalComm(device)
     backend = dist.get_backend()
     import os
-    want_symm = kind == "symm" or (kind == "auto" and os.environ.get("FLUTE_COMM", "") == "symm")
+    # auto: the fused P2P transport (one kernel on the server gathers, reduces, updates and re-broadcasts through NVLink
+    # peer mappings) whenever symmetric memory can be set up; NCCL broadcast/reduce is the fallback / baseline
+    # (``comm: collective`` or FLUTE_COMM=collective).
+    env = os.environ.get("FLUTE_COMM", "")
+    if kind == "auto" and env in ("symm", "collective"):
+        kind = env if env == "collective" else "auto_symm"
+    want_symm = kind in ("symm", "auto", "auto_symm")
     if want_symm and backend == "nccl" and torch.cuda.is_available():
         try:
             from .symm import SymmComm
