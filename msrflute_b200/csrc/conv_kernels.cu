@@ -383,11 +383,15 @@ static void check_arena(const at::Tensor& a, int64_t S) {
 namespace tcv {
 using namespace tc;
 
-constexpr int TM = 128, TN = 64, TK = 32, T_UMMA_K = 8, T_STAGES = 4;
+constexpr int TM = 128, TN = 64, TK = 32, T_UMMA_K = 8;
+// N-tile width is a template parameter: 64 (2 CTAs/SM), 128 (3 stages, 2 CTAs/SM) or 256 (1 CTA/SM).  A wide tile gathers
+// the expensive A operand (im2col rows) ONCE for all output channels instead of once per 64 of them.
+constexpr int t_stages(int tn) { return tn == 128 ? 3 : 4; }
+constexpr int t_stage_bytes(int tn) { return TM * TK * 4 + tn * TK * 4; }
 constexpr int T_PRODUCERS = 256, T_THREADS = 288;
-constexpr int T_A_BYTES = TM * TK * 4, T_B_BYTES = TN * TK * 4, T_STAGE_BYTES = T_A_BYTES + T_B_BYTES;
+constexpr int T_A_BYTES = TM * TK * 4;
 constexpr int T_TABLE_BYTES = TM * 8 + 64 * 8 + 64 * 4;    // wgrad row table + per-tap (offset, kh, kw) table + tap ids
-constexpr int T_SMEM = T_STAGES * T_STAGE_BYTES + T_TABLE_BYTES + 256 + 1024;
+constexpr int t_smem(int tn) { return t_stages(tn) * t_stage_bytes(tn) + T_TABLE_BYTES + 256 + 1024; }
 enum { FPROP = 0, DGRAD = 1, WGRAD = 2 };
 
 __device__ __forceinline__ void st_elem(uint8_t* tile, int row, int e, float v) {     // element e (0..31) of a tile row
@@ -395,10 +399,11 @@ __device__ __forceinline__ void st_elem(uint8_t* tile, int row, int e, float v) 
 }
 
 // in0/in1/out per mode:  FPROP: x, w, y   DGRAD: dy, w, dx   WGRAD: x, dy, dw(grad arena, accumulated)
-template <int MODE>
-__global__ void __launch_bounds__(T_THREADS, 2)
+template <int MODE, int TNW>
+__global__ void __launch_bounds__(T_THREADS, TNW == 256 ? 1 : 2)
 conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out, const ConvP p,
                const int vec_b) {
+  constexpr int T_STAGES = t_stages(TNW), T_STAGE_BYTES = t_stage_bytes(TNW), TN = TNW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   int2* row_table = reinterpret_cast<int2*>(smem + T_STAGES * T_STAGE_BYTES);
@@ -540,7 +545,7 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
           // unpruned filter with a 16-byte aligned row pitch: the reduction index IS the memory index
           const int chunk = tid & 7;
 #pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
+          for (int pass = 0; pass < TN / 32; ++pass) {
             const int brow = (tid >> 3) + pass * 32, n = c_tile0 + brow, kk = r0 + chunk * 4;
             float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (n < C && kk < RED) wv = __ldg(reinterpret_cast<const float4*>(b_src + static_cast<long long>(n) * RED + kk));
@@ -560,8 +565,8 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
           const long long row_pitch = MODE == FPROP ? static_cast<long long>(p.Cin) * (p.compact ? p.ntaps : KHW)
                                                     : (p.compact ? p.ntaps : KHW);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int brow = warp * 8 + i, n = c_tile0 + brow;
+          for (int i = 0; i < TN / 8; ++i) {
+            const int brow = warp * (TN / 8) + i, n = c_tile0 + brow;
             const bool okb = woff >= 0 && n < C;
             const float wv = __ldg(b_src + (okb ? woff + n * row_pitch : 0));
             st_elem(sb, brow, lane, okb ? wv : 0.f);
@@ -588,8 +593,8 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
           st_elem(sa, arow, lane, ok ? xv : 0.f);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int brow = warp * 8 + i, co = c_tile0 + brow;
+        for (int i = 0; i < TN / 8; ++i) {
+          const int brow = warp * (TN / 8) + i, co = c_tile0 + brow;
           const bool okd = mv && co < C;
           const float dv = __ldg(b_src + (okd ? dypart + co * HoWo : 0));
           st_elem(sb, brow, lane, okd ? dv : 0.f);
@@ -602,10 +607,13 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
     if (nst > 0) {
       mbar_wait(acc_bar, 0);
       tc_fence_after();
-      const int q = warp & 3, chalf = warp >> 2;     // TMEM lane quadrant of this warp, 32-column half
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(chalf * 32), v);
+      const int q = warp & 3, chalf = warp >> 2;     // TMEM lane quadrant of this warp, which half of the columns
       const int rr = r_tile0 + q * 32 + lane;
+#pragma unroll 1
+      for (int cc0 = 0; cc0 < TN / 2; cc0 += 32) {
+      const int col0 = chalf * (TN / 2) + cc0;       // first accumulator column of this chunk
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(col0), v);
       if (rr < R) {
         if (MODE == WGRAD) {
           const int ci = rr / p.ntaps, t = p.taps[rr - ci * p.ntaps];
@@ -614,7 +622,7 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
           const long long pitch = p.compact ? static_cast<long long>(R) : static_cast<long long>(p.Cin) * KHW;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int co = c_tile0 + chalf * 32 + j;
+            const int co = c_tile0 + col0 + j;
             if (co < C) atomicAdd(dst + co * pitch, __uint_as_float(v[j]));
           }
         } else {
@@ -627,7 +635,7 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
             r = (cls_h0 + 2 * jh) * p.Wi + cls_w0 + 2 * jw;
           }
           float* dst = out + (static_cast<long long>(slot) * p.B + b) * C * HW + r;
-          const int n_base = c_tile0 + chalf * 32;
+          const int n_base = c_tile0 + col0;
           dst += static_cast<long long>(n_base) * HW;
           if (p.splits > 1) {
 #pragma unroll
@@ -640,6 +648,7 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
           }
         }
       }
+      }  // column chunks
     }
   } else if (lane == 0) {
     // ------------------------------------------------------------------------------------------ MMA issuer
@@ -666,13 +675,13 @@ conv_tc_kernel(const float* __restrict__ in0, const float* __restrict__ in1, flo
   }
 }
 
-static int pick_splits_tc(long long tiles, int stages) {
+static int pick_splits_tc(long long tiles, int stages, int ctas_per_sm = 2) {
   // These launches are latency-bound: a CTA costs a fixed prologue/epilogue (barriers, TMEM allocation, tap masks,
   // accumulator read-out) plus ~1.2 us per 32-deep stage, and 2 CTAs are resident per SM (2 x 98 KB smem).  Splitting the
   // reduction shortens the per-CTA chain but a grid of 300 CTAs on 296 slots runs as TWO waves; pick the split count that
   // minimises  waves x (fixed + stages_per_cta x stage)  (+ the zero-fill / atomic combine when splitting at all).
   const double fixed_us = 5.0, stage_us = 1.2, combine_us = 1.5;
-  const long long slots = 148LL * 2;
+  const long long slots = 148LL * ctas_per_sm;
   int best = 1;
   double best_cost = 1e30;
   for (int s = 1; s <= std::min(32, std::max(1, stages)); ++s) {
@@ -684,17 +693,37 @@ static int pick_splits_tc(long long tiles, int stages) {
   return best;
 }
 
-template <int MODE>
-static void launch_tc(const float* in0, const float* in1, float* out, const ConvP& p, int rows, int cols, int vec_b,
-                      int row_tiles = -1) {
+template <int MODE, int TNW>
+static void launch_tc_w(const float* in0, const float* in1, float* out, const ConvP& p, int rows, int cols, int vec_b,
+                        int row_tiles) {
   static bool configured = false;
   if (!configured) {
-    FLUTE_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
+    FLUTE_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<MODE, TNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem(TNW)));
     configured = true;
   }
-  dim3 grid(row_tiles >= 0 ? row_tiles : (rows + TM - 1) / TM, (cols + TN - 1) / TN, p.S * p.splits);
-  conv_tc_kernel<MODE><<<grid, T_THREADS, T_SMEM, at::cuda::getCurrentCUDAStream()>>>(in0, in1, out, p, vec_b);
+  dim3 grid(row_tiles >= 0 ? row_tiles : (rows + TM - 1) / TM, (cols + TNW - 1) / TNW, p.S * p.splits);
+  conv_tc_kernel<MODE, TNW><<<grid, T_THREADS, t_smem(TNW), at::cuda::getCurrentCUDAStream()>>>(in0, in1, out, p, vec_b);
   FLUTE_CUDA_CHECK(cudaGetLastError());
+}
+
+// N-tile width for `cols` output columns: the widest tile that the columns fill (see t_stages)
+static int pick_tn(int cols) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = std::getenv("FLUTE_CONV_TN");
+    forced = e != nullptr ? std::atoi(e) : 0;
+  }
+  if (forced == 64 || forced == 128 || forced == 256) return forced;
+  return cols >= 256 ? 256 : cols >= 128 ? 128 : 64;
+}
+static int ctas_per_sm(int tn) { return tn == 256 ? 1 : 2; }
+
+template <int MODE>
+static void launch_tc(const float* in0, const float* in1, float* out, const ConvP& p, int rows, int cols, int vec_b,
+                      int tn, int row_tiles = -1) {
+  if (tn == 256) launch_tc_w<MODE, 256>(in0, in1, out, p, rows, cols, vec_b, row_tiles);
+  else if (tn == 128) launch_tc_w<MODE, 128>(in0, in1, out, p, rows, cols, vec_b, row_tiles);
+  else launch_tc_w<MODE, 64>(in0, in1, out, p, rows, cols, vec_b, row_tiles);
 }
 
 }  // namespace tcv
@@ -724,12 +753,13 @@ at::Tensor slot_conv_fprop(at::Tensor x, at::Tensor w_arena, int64_t w_offset, i
   const c10::cuda::CUDAGuard guard(x.device());
   const int M = p.B * p.Ho * p.Wo, K = p.Cin * p.ntaps;
   if (use_tc(M)) {
-    const long long tiles = static_cast<long long>((M + tcv::TM - 1) / tcv::TM) * ((p.Cout + tcv::TN - 1) / tcv::TN) * p.S;
-    p.splits = tcv::pick_splits_tc(tiles, (K + tcv::TK - 1) / tcv::TK);
+    const int tn = tcv::pick_tn(p.Cout);
+    const long long tiles = static_cast<long long>((M + tcv::TM - 1) / tcv::TM) * ((p.Cout + tn - 1) / tn) * p.S;
+    p.splits = tcv::pick_splits_tc(tiles, (K + tcv::TK - 1) / tcv::TK, tcv::ctas_per_sm(tn));
     auto y = p.splits > 1 ? at::zeros({p.S, p.B, p.Cout, p.Ho, p.Wo}, x.options())
                           : at::empty({p.S, p.B, p.Cout, p.Ho, p.Wo}, x.options());
     const int vec_b = (p.ntaps == p.KH * p.KW || p.compact) && (K % 4 == 0) && ((w_offset % 4) == 0) && (w_arena.size(1) % 4 == 0);
-    tcv::launch_tc<tcv::FPROP>(x.data_ptr<float>(), w_arena.data_ptr<float>() + w_offset, y.data_ptr<float>(), p, M, p.Cout, vec_b);
+    tcv::launch_tc<tcv::FPROP>(x.data_ptr<float>(), w_arena.data_ptr<float>() + w_offset, y.data_ptr<float>(), p, M, p.Cout, vec_b, tn);
     return y;
   }
   dim3 grid((M + BM - 1) / BM, (p.Cout + BN - 1) / BN, 1);
@@ -754,7 +784,8 @@ at::Tensor slot_conv_dgrad(at::Tensor dy, at::Tensor w_arena, int64_t w_offset, 
   const c10::cuda::CUDAGuard guard(dy.device());
   const int M = p.B * p.Hi * p.Wi, K = p.Cout * p.ntaps;
   if (use_tc(M)) {
-    const int n_tiles = (p.Cin + tcv::TN - 1) / tcv::TN;
+    const int tn = tcv::pick_tn(p.Cin);
+    const int n_tiles = (p.Cin + tn - 1) / tn;
     if (p.stride == 2) {
       // parity decomposition (see ConvP): 4 dense sub-problems instead of one 4x larger masked one
       p.ncls = 4;
@@ -778,17 +809,18 @@ at::Tensor slot_conv_dgrad(at::Tensor dy, at::Tensor w_arena, int64_t w_offset, 
       p.cls_tile0[4] = tile0;
       auto dx = at::zeros({p.S, p.B, p.Cin, p.Hi, p.Wi}, dy.options());     // classes without taps stay zero
       if (tile0 > 0) {
-        p.splits = tcv::pick_splits_tc(static_cast<long long>(tile0) * n_tiles * p.S, (p.Cout * max_taps + tcv::TK - 1) / tcv::TK);
+        p.splits = tcv::pick_splits_tc(static_cast<long long>(tile0) * n_tiles * p.S, (p.Cout * max_taps + tcv::TK - 1) / tcv::TK,
+                                       tcv::ctas_per_sm(tn));
         tcv::launch_tc<tcv::DGRAD>(dy.data_ptr<float>(), w_arena.data_ptr<float>() + w_offset, dx.data_ptr<float>(), p, M, p.Cin,
-                                   0, tile0);
+                                   0, tn, tile0);
       }
       return dx;
     }
     const long long tiles = static_cast<long long>((M + tcv::TM - 1) / tcv::TM) * n_tiles * p.S;
-    p.splits = tcv::pick_splits_tc(tiles, (K + tcv::TK - 1) / tcv::TK);
+    p.splits = tcv::pick_splits_tc(tiles, (K + tcv::TK - 1) / tcv::TK, tcv::ctas_per_sm(tn));
     auto dx = p.splits > 1 ? at::zeros({p.S, p.B, p.Cin, p.Hi, p.Wi}, dy.options())
                            : at::empty({p.S, p.B, p.Cin, p.Hi, p.Wi}, dy.options());
-    tcv::launch_tc<tcv::DGRAD>(dy.data_ptr<float>(), w_arena.data_ptr<float>() + w_offset, dx.data_ptr<float>(), p, M, p.Cin, 0);
+    tcv::launch_tc<tcv::DGRAD>(dy.data_ptr<float>(), w_arena.data_ptr<float>() + w_offset, dx.data_ptr<float>(), p, M, p.Cin, 0, tn);
     return dx;
   }
   dim3 grid((M + BM - 1) / BM, (p.Cin + BN - 1) / BN, 1);
@@ -816,9 +848,10 @@ void slot_conv_wgrad(at::Tensor x, at::Tensor dy, at::Tensor g_arena, int64_t g_
   const c10::cuda::CUDAGuard guard(x.device());
   const int M = p.B * p.Ho * p.Wo, K = p.Cin * p.ntaps;
   if (use_tc(M)) {
-    const long long tiles = static_cast<long long>((K + tcv::TM - 1) / tcv::TM) * ((p.Cout + tcv::TN - 1) / tcv::TN) * p.S;
-    p.splits = tcv::pick_splits_tc(tiles, (M + tcv::TK - 1) / tcv::TK);
-    tcv::launch_tc<tcv::WGRAD>(x.data_ptr<float>(), dy.data_ptr<float>(), g_arena.data_ptr<float>() + g_offset, p, K, p.Cout, 0);
+    const int tn = tcv::pick_tn(p.Cout);
+    const long long tiles = static_cast<long long>((K + tcv::TM - 1) / tcv::TM) * ((p.Cout + tn - 1) / tn) * p.S;
+    p.splits = tcv::pick_splits_tc(tiles, (M + tcv::TK - 1) / tcv::TK, tcv::ctas_per_sm(tn));
+    tcv::launch_tc<tcv::WGRAD>(x.data_ptr<float>(), dy.data_ptr<float>(), g_arena.data_ptr<float>() + g_offset, p, K, p.Cout, 0, tn);
     return;
   }
   dim3 grid((p.Cout + BM - 1) / BM, (K + BN - 1) / BN, 1);
