@@ -9,9 +9,13 @@ per-round ``latest_model.tar`` checkpoint.  Synthetic Fed-CIFAR-100-shaped data 
 random-init weights.  For N > 1 launch under ``torch.distributed.run`` (one rank per GPU).
 
 ``value`` is measured through the public API (``OptimizationServer.begin_training / run_rounds``) with HBM-resident
-shards, timed with CUDA events on every rank (max over ranks).  ``e2e`` repeats it with the engine in streaming
-mode: every round's client data is copied host(pinned)→device inside the timed region and the round's loss table is
-read back (it always is).  ``gpu_launches`` counts launches of this repo's own kernels in the timed region.
+shards.  The timed region is bracketed by ``Server.sync_nodes()`` (every rank drains its GPU, records a CUDA event,
+barriers); each rank reports its own device time between its events and the maximum is used.  ``e2e`` repeats the K
+rounds on all ranks with the engines in streaming mode: every round's client shards are copied host(pinned)→device
+inside the timed region and the round's record table is read back (it always is); wall clock around ``run_rounds``.
+``gpu_launches`` counts launches of this repo's own kernels in the timed region (rank 0).  Multi-GPU jobs run 10
+set-up rounds before the W warm-up rounds (peer mappings, CUDA-graph capture on every rank).
+``FLUTE_BENCH_CPU=1`` runs the same protocol on CPU/gloo with a tiny population (control-flow test, no number).
 """
 import os
 import sys
