@@ -60,6 +60,8 @@ std::vector<at::Tensor> quantize_segments(at::Tensor flat, at::Tensor seg, at::T
 at::Tensor local_dp(at::Tensor flat, double max_grad, double sigma, bool clip_only, int64_t seed);
 std::vector<at::Tensor> softmax_ce(at::Tensor logits, at::Tensor target, double grad_scale, int64_t ignore_index, bool want_grad);
 at::Tensor cosine_stats(at::Tensor a, at::Tensor b);
+std::vector<at::Tensor> max_pool2d_fwd(at::Tensor x, int64_t k, int64_t stride, int64_t pad);
+at::Tensor max_pool2d_bwd(at::Tensor dy, at::Tensor arg, int64_t H, int64_t W, int64_t k, int64_t stride, int64_t pad);
 }  // namespace flute
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -92,6 +94,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("local_dp", &flute::local_dp);
   m.def("softmax_ce", &flute::softmax_ce);
   m.def("cosine_stats", &flute::cosine_stats);
+  m.def("max_pool2d_fwd", &flute::max_pool2d_fwd);
+  m.def("max_pool2d_bwd", &flute::max_pool2d_bwd);
   m.def("gru_cell_fwd", &flute::gru_cell_fwd);
   m.def("gru_cell_bwd", &flute::gru_cell_bwd);
   m.def("lstm_cell_fwd", &flute::lstm_cell_fwd);

@@ -6,6 +6,7 @@
 //   local_dp            g <- g * min(1, C/||g||) (or C/||g||) + sigma * N(0,1), Philox       (K15)
 //   softmax_ce          per-row loss and d(logits) of softmax cross-entropy in one kernel    (K7)
 //   cosine_stats        <a,b>, ||a||^2, ||b||^2 in one pass                                  (K19)
+//   max_pool2d          NCHW max-pool fwd (+1-byte argmax) / bwd                             (K8)
 #include <ATen/ATen.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
@@ -189,6 +190,45 @@ __global__ void __launch_bounds__(kThreads) cosine_stats_kernel(const float* __r
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ K8 max-pool
+// NCHW fp32 max-pool with the window argmax kept as one byte per output; the backward routes dy to that input element
+// (windows overlap when stride < kernel, hence atomics on a zeroed dx).  First maximum wins ties, like ATen.
+__global__ void __launch_bounds__(kThreads) max_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                unsigned char* __restrict__ arg, long long total, int H, int W,
+                                                                int Ho, int Wo, int k, int stride, int pad) {
+  const long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
+  if (i >= total) return;
+  const int ow = static_cast<int>(i % Wo), oh = static_cast<int>((i / Wo) % Ho);
+  const long long plane = i / (static_cast<long long>(Wo) * Ho);
+  const float* xp = x + plane * H * W;
+  float best = -FLT_MAX;
+  int bi = 0;
+  for (int kh = 0; kh < k; ++kh) {
+    const int ih = oh * stride - pad + kh;
+    if (ih < 0 || ih >= H) continue;
+    for (int kw = 0; kw < k; ++kw) {
+      const int iw = ow * stride - pad + kw;
+      if (iw < 0 || iw >= W) continue;
+      const float v = xp[ih * W + iw];
+      if (v > best) { best = v; bi = kh * k + kw; }
+    }
+  }
+  y[i] = best;
+  arg[i] = static_cast<unsigned char>(bi);
+}
+
+__global__ void __launch_bounds__(kThreads) max_pool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ arg,
+                                                                float* __restrict__ dx, long long total, int H, int W, int Ho,
+                                                                int Wo, int k, int stride, int pad) {
+  const long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
+  if (i >= total) return;
+  const int ow = static_cast<int>(i % Wo), oh = static_cast<int>((i / Wo) % Ho);
+  const long long plane = i / (static_cast<long long>(Wo) * Ho);
+  const int a = arg[i], ih = oh * stride - pad + a / k, iw = ow * stride - pad + a % k;
+  atomicAdd(dx + plane * H * W + ih * W + iw, dy[i]);
+}
+
 static void check_flat(const at::Tensor& t, const char* name) {
   TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kFloat && t.is_contiguous(), name, " must be a contiguous fp32 CUDA tensor");
 }
@@ -311,6 +351,48 @@ at::Tensor cosine_stats(at::Tensor a, at::Tensor b) {
   }
   FLUTE_CUDA_CHECK(cudaGetLastError());
   return out;
+}
+
+// x [..., H, W] fp32 contiguous -> {y [..., Ho, Wo], argmax (uint8, window index)}
+std::vector<at::Tensor> max_pool2d_fwd(at::Tensor x, int64_t k, int64_t stride, int64_t pad) {
+  using namespace misc;
+  check_flat(x, "x");
+  TORCH_CHECK(x.dim() >= 3 && k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && pad <= k / 2, "max_pool2d_fwd: bad arguments");
+  const int H = static_cast<int>(x.size(-2)), W = static_cast<int>(x.size(-1));
+  const int Ho = (H + 2 * static_cast<int>(pad) - static_cast<int>(k)) / static_cast<int>(stride) + 1;
+  const int Wo = (W + 2 * static_cast<int>(pad) - static_cast<int>(k)) / static_cast<int>(stride) + 1;
+  auto sizes = x.sizes().vec();
+  sizes[sizes.size() - 2] = Ho;
+  sizes[sizes.size() - 1] = Wo;
+  const c10::cuda::CUDAGuard guard(x.device());
+  auto y = at::empty(sizes, x.options());
+  auto arg = at::empty(sizes, x.options().dtype(at::kByte));
+  const long long total = y.numel();
+  if (total > 0)
+    max_pool_fwd_kernel<<<static_cast<int>((total + kThreads - 1) / kThreads), kThreads, 0, at::cuda::getCurrentCUDAStream()>>>(
+        x.data_ptr<float>(), y.data_ptr<float>(), arg.data_ptr<uint8_t>(), total, H, W, Ho, Wo, static_cast<int>(k),
+        static_cast<int>(stride), static_cast<int>(pad));
+  FLUTE_CUDA_CHECK(cudaGetLastError());
+  return {y, arg};
+}
+
+at::Tensor max_pool2d_bwd(at::Tensor dy, at::Tensor arg, int64_t H, int64_t W, int64_t k, int64_t stride, int64_t pad) {
+  using namespace misc;
+  check_flat(dy, "dy");
+  TORCH_CHECK(arg.is_cuda() && arg.scalar_type() == at::kByte && arg.is_contiguous() && arg.numel() == dy.numel());
+  auto sizes = dy.sizes().vec();
+  const int Ho = static_cast<int>(dy.size(-2)), Wo = static_cast<int>(dy.size(-1));
+  sizes[sizes.size() - 2] = H;
+  sizes[sizes.size() - 1] = W;
+  const c10::cuda::CUDAGuard guard(dy.device());
+  auto dx = at::zeros(sizes, dy.options());
+  const long long total = dy.numel();
+  if (total > 0)
+    max_pool_bwd_kernel<<<static_cast<int>((total + kThreads - 1) / kThreads), kThreads, 0, at::cuda::getCurrentCUDAStream()>>>(
+        dy.data_ptr<float>(), arg.data_ptr<uint8_t>(), dx.data_ptr<float>(), total, static_cast<int>(H), static_cast<int>(W), Ho, Wo,
+        static_cast<int>(k), static_cast<int>(stride), static_cast<int>(pad));
+  FLUTE_CUDA_CHECK(cudaGetLastError());
+  return dx;
 }
 
 }  // namespace flute

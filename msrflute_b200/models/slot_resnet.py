@@ -15,6 +15,11 @@ from ..ops.slot_ops import SlotConv2d, SlotGroupNorm, SlotLinear, live_taps
 from .resnet_gn import BasicBlock, Bottleneck, GroupNorm2d, RESNET
 
 
+import os as _os
+
+_SLOT_MAXPOOL = _os.environ.get("FLUTE_SLOT_MAXPOOL", "1") == "1"
+
+
 class SlotBatchedResNet:
     @staticmethod
     def supports(model) -> bool:
@@ -123,7 +128,8 @@ class SlotBatchedResNet:
         net = self.net
         S, B = x.shape[0], x.shape[1]
         x = self._gn(self._conv(x, "conv1", net.conv1), "bn1", net.bn1, relu=True)
-        x4 = F.max_pool2d(x.reshape((S * B,) + tuple(x.shape[2:])), 3, 2, 1)
+        pool = misc_ops.max_pool2d if _SLOT_MAXPOOL else F.max_pool2d     # hand-written K8 kernel (1-byte argmax)
+        x4 = pool(x.reshape((S * B,) + tuple(x.shape[2:])), 3, 2, 1)
         x = x4.view((S, B) + tuple(x4.shape[1:]))
         for li, layer in enumerate((net.layer1, net.layer2, net.layer3, net.layer4), start=1):
             for bi, blk in enumerate(layer):

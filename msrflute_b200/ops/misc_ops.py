@@ -68,3 +68,31 @@ def cosine(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     s = cosine_stats(a, b)
     den = torch.sqrt(s[1] * s[2])
     return torch.where(den > 0, s[0] / den.clamp(min=1e-30), torch.zeros_like(den))
+
+
+# ------------------------------------------------------------------------------------------------ K8 max-pool
+class _MaxPool2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, stride, pad):
+        ext = _ext.load()
+        x = x.contiguous()
+        y, arg = ext.max_pool2d_fwd(x, int(k), int(stride), int(pad))
+        _ext.count_launch(1)
+        ctx.save_for_backward(arg)
+        ctx.cfg = (x.shape[-2], x.shape[-1], int(k), int(stride), int(pad))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (arg,) = ctx.saved_tensors
+        H, W, k, stride, pad = ctx.cfg
+        dx = _ext.load().max_pool2d_bwd(dy.contiguous(), arg, H, W, k, stride, pad)
+        _ext.count_launch(1)
+        return dx, None, None, None
+
+
+def max_pool2d(x: torch.Tensor, kernel_size: int, stride: int, padding: int = 0) -> torch.Tensor:
+    """NCHW fp32 max-pool; CUDA: one forward kernel that also stores a 1-byte window argmax, one backward kernel."""
+    if _ext.use_cuda_kernels(x) and x.dtype == torch.float32 and x.dim() >= 3 and hasattr(_ext.load(), "max_pool2d_fwd"):
+        return _MaxPool2d.apply(x, kernel_size, stride, padding)
+    return torch.nn.functional.max_pool2d(x, kernel_size, stride, padding)

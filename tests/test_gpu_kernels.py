@@ -570,3 +570,20 @@ def test_layer_norm_kernel_matches_torch(shape, dtype, affine):
     assert norm_ops.swap_layer_norm_modules(m) == 1 and isinstance(m[1], norm_ops.FusedLayerNorm)
     assert torch.allclose(m(torch.ones(2, 16, device="cuda")), torch.nn.functional.layer_norm(
         m[0](torch.ones(2, 16, device="cuda")), (32,), m[1].weight, m[1].bias), atol=1e-5)
+
+
+@pytest.mark.parametrize("shape,k,s,p", [((200, 64, 16, 16), 3, 2, 1), ((3, 5, 9, 13), 3, 2, 1), ((2, 4, 8, 8), 2, 2, 0),
+                                         ((2, 3, 7, 7), 3, 1, 1)])
+def test_max_pool2d_kernel_matches_torch(shape, k, s, p):
+    _ext()
+    from msrflute_b200.ops import misc_ops
+    torch.manual_seed(41)
+    x = torch.randn(shape, device="cuda").requires_grad_(True)
+    y = misc_ops.max_pool2d(x, k, s, p)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    x2 = x.detach().clone().requires_grad_(True)
+    y2 = torch.nn.functional.max_pool2d(x2, k, s, p)
+    y2.backward(dy)
+    assert torch.equal(y, y2)
+    assert torch.allclose(x.grad, x2.grad, atol=1e-6), (x.grad - x2.grad).abs().max()
