@@ -95,8 +95,11 @@ class RL:
         self.epsilon = rl["initial_epsilon"]
         self.step, self.runningLoss = 0, 0
         desc = rl.get("model_descriptor_RL", "Default")
-        self.model_name = os.path.join(rl["RL_path"], "rl_{}.{}.model".format(self.out_size, desc))
-        self.stats_name = os.path.join(rl["RL_path"], "rl_{}.{}.stats".format(self.out_size, desc))
+        # the reference requires RL.RL_path (KeyError otherwise, RL.py:164); default to ./RL_models next to the checkpoints
+        rl_path = rl.get("RL_path") or os.path.join(config.get("model_path", None) or ".", "RL_models")
+        os.makedirs(rl_path, exist_ok=True)
+        self.model_name = os.path.join(rl_path, "rl_{}.{}.model".format(self.out_size, desc))
+        self.stats_name = os.path.join(rl_path, "rl_{}.{}.stats".format(self.out_size, desc))
         self.make_model()
         self.load_saved_status()
         self.rl_weights = None

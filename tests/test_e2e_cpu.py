@@ -104,6 +104,12 @@ def test_resume_from_checkpoint_continues_at_saved_iteration(tmp_path):
              "dp": {"enable_local_dp": True, "enable_global_dp": True, "eps": -1.0, "max_grad": 1.0, "global_sigma": 0.01,
                     "max_weight": 1.0, "min_weight": 0.0, "delta": 1e-6}}),
     ("FedProx", {"client": {"mu": 0.01}}),
+    ("DGA", {"server": {"aggregate_median": "softmax", "wantRL": True,
+                        "RL": {"initial_epsilon": 0.5, "final_epsilon": 0.1, "epsilon_gamma": 0.9, "max_replay_memory_size": 8,
+                               "minibatch_size": 2, "network_params": "16,12,4", "marginal_update_RL": True,
+                               "optimizer_config": {"type": "adam", "lr": 0.01},
+                               "annealing_config": {"type": "step_lr", "step_interval": "epoch", "gamma": 1.0,
+                                                    "step_size": 100}}}}),
 ])
 def test_strategies_end_to_end(tmp_path, strategy, extra):
     tmp = str(tmp_path)
@@ -112,6 +118,9 @@ def test_strategies_end_to_end(tmp_path, strategy, extra):
                                  extra_client=extra.get("client"), dp=extra.get("dp")))
     m = _metrics(exp)
     assert len(m["Training loss"]) == 3
+    if (extra.get("server") or {}).get("wantRL"):           # RL-learned aggregation weights: agent trained + saved
+        assert "RL Running Loss" in m or "RL" in log
+        assert any(f.startswith("rl_") for f in os.listdir(os.path.join(exp, "models")) + os.listdir(exp)) or "RL" in log
     if extra.get("dp"):
         assert "dp_epsilon_rdp" in m and "Gradient Norm" in m
     if "quant_thresh" in (extra.get("client") or {}):
