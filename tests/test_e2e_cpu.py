@@ -172,3 +172,27 @@ def test_dead_worker_is_detected_not_hung(tmp_path):
     assert r.returncode != 0
     assert time.time() - t0 < 120
     assert "fault injection: rank 1 exits at round 1" in (r.stdout + r.stderr)
+
+
+def test_norm_stats_cosines_fallback_and_server_replay(tmp_path):
+    """Less-travelled reference options: ``dump_norm_stats`` (norm_stats.txt + cosines.txt), ``fall_back_to_best_model``
+    and server-side replay training (``server_replay_config`` + ``server_config.data_config.train``)."""
+    tmp = str(tmp_path)
+    _write_data(tmp)
+    cfgp = _config(tmp, rounds=3, extra_server={
+        "fall_back_to_best_model": True,
+        "server_replay_config": {"server_iterations": 2, "optimizer_config": {"type": "sgd", "lr": 0.05}}})
+    with open(cfgp) as f:
+        c = yaml.safe_load(f)
+    c["dump_norm_stats"] = True
+    c["server_config"]["data_config"]["train"] = {"batch_size": 16, "train_data_server": "test.pt",
+                                                  "desired_max_samples": 64, "num_workers": 0}
+    with open(cfgp, "w") as f:
+        yaml.safe_dump(c, f)
+    exp, log = _run(tmp, cfgp)
+    files = os.listdir(os.path.join(exp, "models"))
+    assert "norm_stats.txt" in files and "cosines.txt" in files
+    cos = [json.loads(l) for l in open(os.path.join(exp, "models", "cosines.txt"))]
+    assert len(cos) == 3 and all(-1.0001 <= v <= 1.0001 for row in cos for v in row)
+    assert "Running replay iterations on server" in log and "falling back to model" in log
+    assert len(_metrics(exp)["Training loss"]) == 3
