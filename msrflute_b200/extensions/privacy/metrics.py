@@ -25,7 +25,21 @@ def extract_indices_from_embeddings(gradients, batch, embed_size, vocab_size):
 
 
 def compute_perplexity(encoded_batch, model):
+    """Per-token log-likelihood ``[batch, seq]`` of ``encoded_batch`` under ``model``.
+
+    The reference reads ``model.inference(batch)['output']`` as a ``[batch, seq, vocab]`` logit tensor
+    (``metrics.py:25-30``) — which none of its shipped models return (the GRU LM returns a dict of top-k
+    probabilities or ``None``), so the leakage metric cannot run there.  Here a model may expose
+    ``token_logits(batch) -> (logits [b, s, v], targets [b, s], mask [b, s])``; otherwise a 3-D ``output`` tensor is
+    used the reference's way."""
+    if hasattr(model, "token_logits"):
+        logits, targets, mask = model.token_logits(encoded_batch)
+        logp = T.nn.functional.log_softmax(logits.float(), dim=-1)
+        ll = logp.gather(-1, targets.clamp(min=0).long().unsqueeze(-1)).squeeze(-1)
+        return T.where(mask, ll, T.zeros_like(ll))
     out = model.inference(encoded_batch)["output"]
+    if not T.is_tensor(out) or out.dim() != 3:
+        raise TypeError("privacy leakage metric needs per-token logits: give the model a token_logits(batch) method")
     b, s, v = out.shape
     logp = T.nn.functional.log_softmax(out, dim=-1)
     tgt = encoded_batch.reshape(b, s, 1).to(logp.device).long()

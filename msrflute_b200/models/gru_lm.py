@@ -87,6 +87,15 @@ class GRU(BaseModel):
         m = mask.reshape(-1)
         return output.reshape(-1, self.vocab_size)[m], x.reshape(-1)[m], x.shape[0]
 
+    def token_logits(self, input):
+        """Per-position logits ``[b, s, v]`` (position t predicts token t from tokens < t: the recurrence starts from
+        a zero step), their targets and the non-pad mask — what the privacy leakage metric needs."""
+        x = self._tokens(input)
+        mask = x >= 0
+        x = x * mask.long()
+        output, _ = self.forward(x[:, :-1])
+        return output, x, mask
+
     def loss(self, input) -> Tensor:
         preds, targets, _ = self._preds_targets(input)
         return T.nn.functional.cross_entropy(preds, targets)

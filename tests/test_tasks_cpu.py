@@ -62,3 +62,27 @@ def test_experiment_config_two_rounds(task, tmp_path):
     p = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
     _finite_training_loss(os.path.join(out, "smoke"))
+
+
+def test_privacy_attack_metrics_on_word_level_model(tmp_path):
+    """``privacy_metrics_config.apply_metrics``: embedding-gradient index extraction, word-rank statistic and the
+    practical-epsilon leakage attack run on the GRU LM (the reference's leakage metric cannot run on its own model:
+    it expects a logit tensor its ``inference`` never returns) and their aggregates are logged per round."""
+    out = str(tmp_path)
+    with open(os.path.join(ROOT, "testing", "hello_world_nlg_gru.yaml")) as f:
+        cfg = yaml.safe_load(f)
+    cfg["privacy_metrics_config"] = {
+        "apply_metrics": True, "apply_indices_extraction": True, "allowed_word_rank": 100, "apply_leakage_metric": True,
+        "max_leakage": 30.0, "adaptive_leakage_threshold": 0.95, "is_leakage_weighted": True,
+        "attacker_optimizer_config": {"lr": 0.03, "type": "adamax", "amsgrad": False}}
+    cfg_path = os.path.join(out, "config.yaml")
+    with open(cfg_path, "w") as f:
+        yaml.safe_dump(cfg, f)
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", FLUTE_ALLOW_FALLBACK="1")
+    cmd = [sys.executable, os.path.join(ROOT, "e2e_trainer.py"), "-dataPath", out, "-outputPath", out, "-config", cfg_path,
+           "-task", "nlg_gru", "-backend", "gloo", "-experiment", "pm"]
+    p = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+    keys = {json.loads(l)["k"] for l in open(os.path.join(out, "pm", "log", "metrics.jsonl"))}
+    assert {"Practical epsilon (Max leakage)", "Extracted indices percentage", "Dropped clients"} <= keys
+    assert any(k.startswith("Words percentage above") for k in keys)
