@@ -302,13 +302,22 @@ def make_lr_scheduler(annealing_config, optimizer, num_batches=1):
         if interval == "epoch":
             cfg["step_size"] = int(num_batches * cfg["step_size"])
         return sched.StepLR(optimizer=optimizer, **cfg)
+    # The schema makes ``gamma`` and ``step_size`` REQUIRED for the server's annealing block (``schema.py``), and the
+    # reference forwards every key to the scheduler — so ``multi_step_lr`` / ``val_loss`` raise TypeError there on any
+    # valid server config.  Here the keys a scheduler does not take are dropped / mapped.
     if kind == "multi_step_lr":
+        cfg.pop("step_size", None)
         if interval == "epoch":
             cfg["milestones"] = [int(i * num_batches) for i in cfg["milestones"]]
         return sched.MultiStepLR(optimizer=optimizer, **cfg)
     if kind == "rampup-keep-expdecay-keep":
+        cfg.pop("gamma", None)
+        cfg.pop("step_size", None)
         return RampupKeepExpdecayKeepLRScheduler(optimizer=optimizer, **cfg)
     if kind == "val_loss":
+        gamma, step_size = cfg.pop("gamma", None), cfg.pop("step_size", None)
+        cfg.setdefault("factor", gamma if gamma is not None and 0 < gamma < 1 else 0.1)
+        cfg.setdefault("patience", int(step_size) if step_size is not None else 10)
         return sched.ReduceLROnPlateau(optimizer, **cfg)
     raise ValueError("{} LR scheduler not supported".format(kind))
 

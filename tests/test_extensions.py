@@ -184,3 +184,24 @@ def test_rl_agent_forward_train_save_load(tmp_path):
     assert rl2.cur_iter_no == 4
     for p, q in zip(rl.model.parameters(), rl2.model.parameters()):
         assert torch.equal(p.cpu(), q.cpu())
+
+
+def test_lr_scheduler_factory_accepts_schema_mandated_keys():
+    """gamma / step_size are required by the server annealing schema; every scheduler type must tolerate them."""
+    import torch
+    from msrflute_b200.utils import make_lr_scheduler
+    p = [torch.nn.Parameter(torch.zeros(1))]
+    base = {"step_interval": "epoch", "gamma": 0.5, "step_size": 2}
+    s = make_lr_scheduler(dict(base, type="step_lr"), torch.optim.SGD(p, lr=1.0))
+    assert isinstance(s, torch.optim.lr_scheduler.StepLR)
+    s = make_lr_scheduler(dict(base, type="multi_step_lr", milestones=[1, 3]), torch.optim.SGD(p, lr=1.0))
+    assert isinstance(s, torch.optim.lr_scheduler.MultiStepLR) and list(s.milestones) == [1, 3]
+    s = make_lr_scheduler(dict(base, type="rampup-keep-expdecay-keep", peak_lr=0.05, floor_lr=0.001, sr=1, si=2, sf=3),
+                          torch.optim.SGD(p, lr=1.0))
+    assert abs(s.lr_at(1) - 0.05) < 1e-9 and abs(s.lr_at(10) - 0.001) < 1e-9
+    opt = torch.optim.SGD(p, lr=1.0)
+    s = make_lr_scheduler(dict(base, type="val_loss"), opt)
+    assert isinstance(s, torch.optim.lr_scheduler.ReduceLROnPlateau) and s.factor == 0.5 and s.patience == 2
+    for loss in (1.0, 1.0, 1.0, 1.0):
+        s.step(loss)
+    assert opt.param_groups[0]["lr"] == 0.5
