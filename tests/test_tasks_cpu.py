@@ -86,3 +86,39 @@ def test_privacy_attack_metrics_on_word_level_model(tmp_path):
     keys = {json.loads(l)["k"] for l in open(os.path.join(out, "pm", "log", "metrics.jsonl"))}
     assert {"Practical epsilon (Max leakage)", "Extracted indices percentage", "Dropped clients"} <= keys
     assert any(k.startswith("Words percentage above") for k in keys)
+
+
+def _run_cfg(task, cfg, out, name):
+    cfg_path = os.path.join(out, "config.yaml")
+    with open(cfg_path, "w") as f:
+        yaml.safe_dump(cfg, f)
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", FLUTE_ALLOW_FALLBACK="1", FLUTE_SYNTH_USERS="12")
+    cmd = [sys.executable, os.path.join(ROOT, "e2e_trainer.py"), "-dataPath", out, "-outputPath", out, "-config", cfg_path,
+           "-task", task, "-backend", "gloo", "-experiment", name]
+    p = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+    return {json.loads(l)["k"] for l in open(os.path.join(out, name, "log", "metrics.jsonl"))}
+
+
+def test_baseline_config4_shakespeare_with_quantized_gather(tmp_path):
+    """BASELINE.json config #4 in miniature: LSTM char-LM, DGA with gradient quantization on the gather path."""
+    with open(os.path.join(ROOT, "experiments", "nlp_rnn_fedshakespeare", "config.yaml")) as f:
+        cfg = _shrink(yaml.safe_load(f))
+    cfg["strategy"] = "DGA"
+    cfg["server_config"]["aggregate_median"] = "mean"
+    cfg["client_config"].update({"quant_thresh": 0.3, "quant_bits": 8, "quant_anneal": 0.95})
+    keys = _run_cfg("nlp_rnn_fedshakespeare", cfg, str(tmp_path), "q")
+    assert {"Quantization Thresh.", "Training loss"} <= keys
+
+
+def test_baseline_config5_bert_mlm_with_global_dp(tmp_path):
+    """BASELINE.json config #5 in miniature: BERT MLM, DGA aggregation with client clipping + server Gaussian noise and
+    RDP accounting logged every round."""
+    with open(os.path.join(ROOT, "testing", "hello_world_mlm_bert.yaml")) as f:
+        cfg = yaml.safe_load(f)
+    cfg["strategy"] = "DGA"
+    cfg["server_config"]["aggregate_median"] = "mean"
+    cfg["dp_config"] = {"enable_local_dp": True, "enable_global_dp": True, "eps": -1.0, "max_grad": 1.0, "global_sigma": 0.01,
+                        "max_weight": 1.0, "min_weight": 0.0, "delta": 1e-6, "weight_scaler": 1.0}
+    keys = _run_cfg("mlm_bert", cfg, str(tmp_path), "dp")
+    assert {"Gradient Norm", "dp_epsilon_rdp", "dp_sigma", "Training loss"} <= keys
