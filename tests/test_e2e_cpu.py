@@ -196,3 +196,24 @@ def test_norm_stats_cosines_fallback_and_server_replay(tmp_path):
     assert len(cos) == 3 and all(-1.0001 <= v <= 1.0001 for row in cos for v in row)
     assert "Running replay iterations on server" in log and "falling back to model" in log
     assert len(_metrics(exp)["Training loss"]) == 3
+
+
+@pytest.mark.parametrize("name,strategy,server,b200,nproc", [
+    ("individual_payloads", "DGA", {"aggregate_median": "softmax", "stale_prob": 0.3}, None, 2),   # per-client flat payloads on the wire
+    ("reference_layout", "FedAvg", {}, {"server_is_worker": False, "dispatch": "dynamic"}, 3),        # rank 0 = server only
+])
+def test_multi_rank_variants(tmp_path, name, strategy, server, b200, nproc):
+    tmp = str(tmp_path)
+    _write_data(tmp)
+    cfgp = _config(tmp, rounds=3, strategy=strategy, extra_server=server)
+    if b200:
+        with open(cfgp) as f:
+            c = yaml.safe_load(f)
+        c["server_config"]["b200"] = b200
+        with open(cfgp, "w") as f:
+            yaml.safe_dump(c, f)
+    exp, log = _run(tmp, cfgp, nproc=nproc, port=29731 + nproc)
+    st = json.load(open(os.path.join(exp, "models", "status_log.json")))
+    assert st["i"] == 3
+    m = _metrics(exp)
+    assert len(m["Training loss"]) == 3 and m["Val loss"][-1] < m["Val loss"][0]
