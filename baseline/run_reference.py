@@ -131,6 +131,15 @@ def main():
           "higher_is_better": True, "scaling": "strong", "vs_baseline": value / BASELINE_PUBLISHED_ROUNDS_PER_SEC,
           "dtype": "fp32(tf32 conv)", "data": "synthetic Fed-CIFAR-100 shape (500 users x 100 x 32x32x3 uint8), random-init weights",
           "clocks": state["clocks"],
+          # the reference IS end to end: every mini-batch is moved host->device inside model.loss() and every step
+          # copies the loss (and all gradients, trainer.py:277-288) back; so its e2e number is its wall clock
+          "e2e": {"value": args.steps / (wall_ms / 1e3), "unit": "rounds/s",
+                  "h2d_bytes_per_step": args.clients_per_round * 100 * (3 * 32 * 32 * 4 + 8),
+                  "d2h_bytes_per_step": args.clients_per_round * (5 * (11689512 * 4 + 4) + 11689512 * 4),
+                  "note": "wall clock between the reference's own per-round log calls; bytes counted from its code path "
+                          "(float32 batches H2D per step; per-step gradient statistics + loss and the per-client "
+                          "payload D2H)"},
+          "gpu_launches": None,
           "config": {"model": "reference RESNET as shipped (resnet18, BatchNorm2d, 1000-way FC)",
                      "clients_per_round": args.clients_per_round, "client_batch": 20, "local_steps_per_client": 5,
                      "global_batch": args.clients_per_round * 100, "seq_len": None,

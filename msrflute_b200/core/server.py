@@ -476,7 +476,8 @@ class OptimizationServer(federated.Server):
         if is_dga and dp.get("enable_global_dp", False):
             assert dp["enable_local_dp"], "global DP requires enable_local_dp (client-side clipping)"
             noise_scale = dp["global_sigma"] * dp["max_grad"] / num_clients_curr_iter
-            seed = (int(self.config["server_config"].get("b200", {}).get("seed", 0)) << 32) ^ (curr_iter + 1)
+            from ..extensions.privacy import rng as dp_rng
+            seed = dp_rng.dp_seed(stream=2)      # fresh OS entropy every round — never the reproducibility seed
             stats_out = torch.zeros(2, device=worker.accumulator().device)
         if wsum is None:
             wsum = torch.tensor(float(sum(weights)), device=worker.accumulator().device)

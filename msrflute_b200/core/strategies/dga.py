@@ -54,7 +54,7 @@ class DGA(BaseStrategy):
             self.rl = None
             if self.want_rl:
                 from ...extensions.RL import RL
-                self.rl = RL(config=self.server_config)
+                self.rl = RL(config=self.server_config, model_path=self.model_path)
             self.client_parameters_stack = []
             self.client_parameters_stack_stale = []
             self.client_weights = []

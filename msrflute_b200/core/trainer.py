@@ -134,31 +134,55 @@ class ModelUpdater(TrainerBase):
         g = opt.param_groups[0]
         if g.get("amsgrad", False) or g.get("maximize", False) or not next(self.model.parameters()).is_cuda:
             return None
-        if len(opt.state) != 0:
-            return None                  # resumed state lives in per-tensor buffers; keep the torch path
         w = ar[0]
         st = arena_ops.ServerOptState(
             kind, w.flat.numel(), w.flat.device, lr=g["lr"], betas=g.get("betas", (0.9, 0.999)),
             eps=g.get("eps", 1e-8), weight_decay=g.get("weight_decay", 0.0) or 0.0, momentum=g.get("momentum", 0.0) or 0.0,
             dampening=g.get("dampening", 0.0) or 0.0, nesterov=g.get("nesterov", False),
             correct_bias=g.get("correct_bias", True))
-        lay = w.layout
+        self._fused = (st, w.layout.segments(w.flat.device))
+        self._fused_kind = kind
+        self._bind_fused_state()
+        # Any later ``optimizer.load_state_dict`` (``ModelUpdater.load`` — called every round by
+        # ``fall_back_to_prev_best_status`` — or the RL path) replaces the state entries with fresh tensors: import
+        # them into the arenas and re-point the entries, otherwise the fused kernel would keep updating orphaned
+        # buffers and checkpoints would carry frozen optimizer state.
+        if not getattr(self, "_fused_hook", None):
+            self._fused_hook = opt.register_load_state_dict_post_hook(lambda _o: self._bind_fused_state())
+        return self._fused
+
+    def _bind_fused_state(self):
+        """Copy whatever per-parameter state the torch optimizer currently holds (fresh, resumed from a checkpoint
+        or just re-loaded) into the arena-resident state and re-point ``optimizer.state`` at views of the arenas."""
+        if getattr(self, "_fused", None) is None:
+            return
+        st, kind, opt = self._fused[0], self._fused_kind, self.optimizer
+        lay = module_arena(self.model)[0].layout
         mv = lay.views(st.m) if st.m is not None else None
         vv = lay.views(st.v) if st.v is not None else None
+        v_key = "exp_inf" if kind == "adamax" else "exp_avg_sq"
+        step = None
         for i, p in enumerate(self.model.parameters()):
             s = opt.state[p]
-            if kind == "sgd":
+            if kind in ("sgd", "LarsSGD"):
                 if st.m is not None:
+                    old = s.get("momentum_buffer")
+                    if torch.is_tensor(old) and old.data_ptr() != mv[i].data_ptr():
+                        mv[i].copy_(old)
+                        st.step = max(st.step, 1)        # a loaded buffer is not a "first step" (buf = grad) any more
                     s["momentum_buffer"] = mv[i]
-            elif kind == "LarsSGD":
-                if st.m is not None:
-                    s["momentum_buffer"] = mv[i]
+                continue
+            for key, views in (("exp_avg", mv), (v_key, vv)):
+                old = s.get(key)
+                if torch.is_tensor(old) and old.data_ptr() != views[i].data_ptr():
+                    views[i].copy_(old)
+                s[key] = views[i]
+            if "step" in s:
+                step = int(s["step"].item()) if torch.is_tensor(s["step"]) else int(s["step"])
             else:
                 s["step"] = 0 if kind in ("adamW", "lamb") else torch.tensor(0.0)
-                s["exp_avg"] = mv[i]
-                s["exp_avg_sq" if kind != "adamax" else "exp_inf"] = vv[i]
-        self._fused = (st, lay.segments(w.flat.device))
-        return self._fused
+        if step is not None:
+            st.step = step
 
     def fused_update(self, accs, weight_sum, noise_scale=0.0, seed=0, bcast=None, stats_out=None, grad_out=None):
         """One fused pass: Σ_ranks acc / Σw (+noise) (+clip) → optimizer → broadcast.  Returns False when the
@@ -173,6 +197,7 @@ class ModelUpdater(TrainerBase):
         arena_ops.server_update(w, accs, weight_sum, st, grad_out=grad_out, noise_scale=noise_scale, seed=seed,
                                 max_grad_norm=self.max_grad_norm, segments=segs, bcast=bcast, zero_accs=True,
                                 stats_out=stats_out)
+        self.optimizer._opt_called = True          # the fused kernel WAS the optimizer step (lr_scheduler order check)
         for p in self.model.parameters():          # keep the per-parameter step counters in sync for checkpoints
             s = self.optimizer.state.get(p)
             if s is not None and "step" in s:

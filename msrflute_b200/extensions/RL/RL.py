@@ -86,7 +86,7 @@ class NeuralNetwork(nn.Module):
 
 
 class RL:
-    def __init__(self, config=None):
+    def __init__(self, config=None, model_path=None):
         self.config = config
         rl = config["RL"]
         self.out_size = config["num_clients_per_iteration"]
@@ -95,8 +95,13 @@ class RL:
         self.epsilon = rl["initial_epsilon"]
         self.step, self.runningLoss = 0, 0
         desc = rl.get("model_descriptor_RL", "Default")
-        # the reference requires RL.RL_path (KeyError otherwise, RL.py:164); default to ./RL_models next to the checkpoints
-        rl_path = rl.get("RL_path") or os.path.join(config.get("model_path", None) or ".", "RL_models")
+        # the reference requires RL.RL_path (KeyError otherwise, RL.py:164); default to RL_models next to the checkpoints
+        # of THIS run (never the working directory: runs must not write into the source tree)
+        base = model_path or config.get("model_path", None)
+        if base is None:
+            import tempfile
+            base = tempfile.mkdtemp(prefix="flute_rl_")
+        rl_path = rl.get("RL_path") or os.path.join(base, "RL_models")
         os.makedirs(rl_path, exist_ok=True)
         self.model_name = os.path.join(rl_path, "rl_{}.{}.model".format(self.out_size, desc))
         self.stats_name = os.path.join(rl_path, "rl_{}.{}.stats".format(self.out_size, desc))

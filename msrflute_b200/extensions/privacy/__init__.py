@@ -22,6 +22,7 @@ from scipy.special import betainc, betaln
 from ...ops import misc_ops
 from ...utils import print_rank
 from . import analysis as privacy_analysis
+from . import rng
 from .analysis import RDPIncrementalAccountant
 
 ORDERS = [1.25, 1.5, 1.75, 2., 2.25, 2.5, 3., 3.5, 4., 4.5] + list(range(5, 64)) + [128, 256, 512]
@@ -64,9 +65,9 @@ def private_unit2(grad, gamma, prob):
     (else from its complement) and debias by 1/m."""
     np.testing.assert_almost_equal(grad.norm().cpu().item(), 1, decimal=5)
     assert prob >= 0.5 and 0 <= gamma <= 1
-    want_cap = bool(T.rand(()) < prob)
+    want_cap = bool(rng.rand(()) < prob)
     while True:
-        V = T.normal(0, 1, grad.shape, device=grad.device)
+        V = rng.randn(grad.shape, device=grad.device)
         V = V / V.norm()
         if bool(T.dot(V, grad) >= gamma) == want_cap:
             break
@@ -80,7 +81,7 @@ def add_private_unit2_noise(eps, grad):
 
 def add_gaussian_noise(grad, eps, max_grad, delta):
     sigma = compute_LDP_noise_std(eps, max_grad, delta)
-    return grad + sigma * T.randn(grad.shape, device=grad.device), sigma
+    return grad + sigma * rng.randn(grad.shape, device=grad.device), sigma
 
 
 def scalar_DP(r, eps, k, r_max):
@@ -88,11 +89,11 @@ def scalar_DP(r, eps, k, r_max):
     r = np.minimum(r, r_max)
     val = k * r / r_max
     lo, hi = math.floor(val), math.ceil(val)
-    J = lo if T.rand(()) < (hi - val) else hi
+    J = lo if rng.rand(()) < (hi - val) else hi
     e = np.exp(eps)
-    if T.rand(()) >= e / (e + k):
+    if rng.rand(()) >= e / (e + k):
         while True:
-            J_ = T.randint(0, k + 1, ()).item()
+            J_ = int(T.randint(0, k + 1, (), generator=rng.dp_generator()).item())
             if J_ != J:
                 J = J_
                 break
@@ -102,7 +103,8 @@ def scalar_DP(r, eps, k, r_max):
 
 
 def laplace_noise(max_sens, eps, vocab_size):
-    return np.random.laplace(0.0, max_sens / eps, vocab_size)
+    u = rng.rand((int(vocab_size),)).double().numpy() - 0.5          # inverse-CDF sampling from the DP generator
+    return -(max_sens / eps) * np.sign(u) * np.log1p(-2.0 * np.abs(u))
 
 
 # ------------------------------------------------------------ flat grad access
@@ -147,9 +149,9 @@ def apply_global_dp(config, model, num_clients_curr_iter, select_grad=True, metr
     noise_scale = dp["global_sigma"] * dp["max_grad"] / num_clients_curr_iter
     grad_norm = flat.norm()
     if writer is None:
-        flat.add_(T.randn_like(flat), alpha=noise_scale)
+        flat.add_(rng.randn_like(flat), alpha=noise_scale)
     else:
-        writer(flat + T.randn_like(flat) * noise_scale)
+        writer(flat + rng.randn_like(flat) * noise_scale)
     if metric_logger is not None:
         metric_logger("Gradient Norm", grad_norm.item())
     return noise_scale
@@ -179,12 +181,12 @@ def apply_local_dp(trainer, weight, dp_config, add_weight_noise):
     sigma = compute_LDP_noise_std(eps, sens, delta)
     scale = max_grad / grad_norm
     if fused:                                                # scale to C and add Philox Gaussian noise in one pass
-        misc_ops.local_dp_(flat, max_grad, float(sigma), False, seed=int(T.randint(0, 2 ** 62, (1,)).item()))
+        misc_ops.local_dp_(flat, max_grad, float(sigma), False, seed=rng.dp_seed(stream=1))
     elif writer is None:
-        flat.mul_(scale).add_(T.randn_like(flat), alpha=float(sigma))
+        flat.mul_(scale).add_(rng.randn_like(flat), alpha=float(sigma))
     else:
-        writer(flat * scale + float(sigma) * T.randn_like(flat))
-    noisy_w = w_scaled + float(sigma) * T.randn(()).item()
+        writer(flat * scale + float(sigma) * rng.randn_like(flat))
+    noisy_w = w_scaled + float(sigma) * rng.randn(()).item()
     weight = min(max(noisy_w, dp_config["min_weight"]), dp_config["max_weight"]) / scaler
     if not add_weight_noise:
         weight = weight_in

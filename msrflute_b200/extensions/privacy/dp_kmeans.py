@@ -11,6 +11,8 @@ import numpy as np
 import torch
 from scipy.special import gammainc
 
+from . import rng
+
 
 def sample(ndim, r, num_samples=1):
     """Uniform samples from the ``ndim``-ball of radius ``r``."""
@@ -49,9 +51,9 @@ def add_gaussian_noise(centers_new, weight_in_clusters, eps, max_cluster_l2, max
         scaler = max_cluster_l2 / (max_sample_weight * cluster_to_weight_ratio)
     msw = max_sample_weight * scaler
     sigma = np.sqrt(2 * np.log(1.25 / delta)) * np.sqrt(max_cluster_l2 ** 2 + msw ** 2) / eps
-    sums = centers_new * weight_in_clusters.reshape(-1, 1) + np.random.normal(scale=sigma, size=centers_new.shape)
+    sums = centers_new * weight_in_clusters.reshape(-1, 1) + sigma * rng.randn(tuple(centers_new.shape)).double().numpy()
     weight_in_clusters[:] = np.maximum(
-        1e-10, weight_in_clusters * scaler + np.random.normal(scale=sigma, size=weight_in_clusters.shape)) / scaler
+        1e-10, weight_in_clusters * scaler + sigma * rng.randn(tuple(weight_in_clusters.shape)).double().numpy()) / scaler
     centers_new[:] = sums / weight_in_clusters.reshape(-1, 1)
     return sigma
 

@@ -71,8 +71,12 @@ _PINNED = {}
 
 
 def _to_host(obj):
-    """D2H of a snapshot: one pinned staging buffer per distinct device storage (reused by the single writer thread)."""
+    """D2H of a snapshot: one pinned staging buffer per distinct device storage.  Buffers are pooled by
+    ``(nbytes, ordinal)`` — a checkpoint usually holds several storages of the SAME size (the parameter arena and the
+    Adam ``m`` / ``v`` arenas, or ``exp_avg`` / ``exp_avg_sq`` of every same-shaped layer), and each needs its own
+    staging buffer for the lifetime of the ``torch.save`` call.  The single writer thread reuses the pool between calls."""
     hosts = {}
+    used = {}                              # nbytes -> how many buffers of that size this call already took
 
     def move(t):
         if not t.is_cuda:
@@ -81,13 +85,15 @@ def _to_host(obj):
         if key not in hosts:
             storage = t.untyped_storage()
             n = storage.nbytes()
-            buf = _PINNED.get(n)
+            ordinal = used.get(n, 0)
+            used[n] = ordinal + 1
+            buf = _PINNED.get((n, ordinal))
             if buf is None:
                 try:
                     buf = torch.empty(n, dtype=torch.uint8).pin_memory()
                 except RuntimeError:
                     buf = torch.empty(n, dtype=torch.uint8)
-                _PINNED[n] = buf
+                _PINNED[(n, ordinal)] = buf
             buf.copy_(torch.empty(0, dtype=torch.uint8, device=t.device).set_(storage), non_blocking=False)
             hosts[key] = buf.untyped_storage()
         return torch.empty(0, dtype=t.dtype).set_(hosts[key], t.storage_offset(), t.size(), t.stride())
@@ -125,6 +131,9 @@ class AsyncCheckpointer:
             snap = _snapshot(state, self._stream)
             ev = torch.cuda.Event()
             ev.record(self._stream)
+            # the next in-place weight update (this stream, or a peer's P2P stores ordered behind it) must not start
+            # before the D2D snapshot has been taken
+            torch.cuda.current_stream().wait_event(ev)
         else:
             snap = _snapshot(state, None)
         with self._wake:
