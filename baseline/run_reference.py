@@ -17,7 +17,8 @@ import time
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(HERE, "_ref")
 sys.path.insert(0, HERE)
-from bench_common import BASELINE_PUBLISHED_ROUNDS_PER_SEC, HEADLINE_METRIC, ClockSampler, emit, parse_args  # noqa: E402
+from bench_common import (BASELINE_PUBLISHED, BASELINE_PUBLISHED_ROUNDS_PER_SEC, HEADLINE_METRIC, TASKS, ClockSampler, emit,  # noqa: E402
+                          parse_args)
 
 
 def seed_data(root):
@@ -46,6 +47,8 @@ def seed_data(root):
 
 def main():
     args = parse_args()
+    if args.clients_per_round is None:
+        args.clients_per_round = TASKS[args.task]["clients_per_round"]
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

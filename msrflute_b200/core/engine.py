@@ -45,6 +45,7 @@ import torch
 from ..ops import _ext, arena_ops
 from ..parallel.arena import ArenaLayout, adopt_module, module_arena
 from ..utils import print_rank
+from ..utils.timing import PHASES
 from . import client as client_mod
 
 REC_LOSS, REC_SUM, REC_SUMSQ, REC_COUNT, REC_NS, REC_WEIGHT, REC_STEPS, REC_PAD = range(8)
@@ -187,7 +188,14 @@ class DeviceClientEngine:
         lay = self.layout
         self.has_buffers = any(True for _ in base.buffers())
         self.slot_model = None
-        if self.slot_plan is not None:
+        if self.slot_plan is not None and self.slot_plan.get("kind") == "slotnet":
+            from ..models.slotnet_resnet import SlotNetResNet
+            bs = int(self.config["client_config"]["data_config"]["train"]["batch_size"])
+            self.slot_model = SlotNetResNet(base, self.W, self.G, self.slot_plan, batch=bs)
+            self.param_stack, self.grad_stack, self.param_names, self.loss_module = {}, [], [], None
+            print_rank("device engine: SlotNet (TMA + tcgen05 NHWC program, {} launches per local step) enabled".format(
+                self.slot_model.n_ops), logging.INFO)
+        elif self.slot_plan is not None:
             from ..models.slot_resnet import SlotBatchedResNet
             self.slot_model = SlotBatchedResNet(base, self.layout, self.W, self.G, plan=self.slot_plan)
             self.param_stack, self.grad_stack, self.param_names, self.loss_module = {}, [], [], None
@@ -232,6 +240,10 @@ class DeviceClientEngine:
             return None
         src = self.X if self.resident else self.Xh
         example = self.dataset.transform_batch(src[:2].to(self.device))
+        if _os.environ.get("FLUTE_SLOTNET", "1") != "0":
+            from ..models.slotnet_resnet import SlotNetResNet
+            if SlotNetResNet.supports(base, example):
+                return SlotNetResNet.plan(base, self.layout)
         return SlotBatchedResNet.plan_compact(base, self.layout, example)
 
     def _pack_dataset(self):
@@ -334,8 +346,11 @@ class DeviceClientEngine:
         if self.slot_model is not None:
             S, B = xw.shape[0], xw.shape[1]
             xb = self.dataset.transform_batch(xw.reshape((S * B,) + tuple(xw.shape[2:])))
-            losses = self.slot_model.losses(xb.reshape((S, B) + tuple(xb.shape[1:])), yw)
-            losses.sum().backward()                    # weight grads are accumulated into self.G by the kernels
+            if hasattr(self.slot_model, "step"):       # SlotNet: static forward+backward program, no autograd
+                losses = self.slot_model.step(xb, yw)
+            else:
+                losses = self.slot_model.losses(xb.reshape((S, B) + tuple(xb.shape[1:])), yw)
+                losses.sum().backward()                # weight grads are accumulated into self.G by the kernels
             arena_ops.fused_client_step(self.W, self.G, self.hyper, self.stats, self.M, n_logical=self.layout.numel,
                                         nesterov=self.nesterov, dampening=self.dampening, zero_grad=True,
                                         first_step=self.first)
@@ -424,10 +439,11 @@ class DeviceClientEngine:
         for wave_start in range(0, len(client_ids), self.S):
             wave = client_ids[wave_start:wave_start + self.S]
             n_act = len(wave)
-            if self.index_map is not None:
-                arena_ops.scatter_in(self.W, w_global, self.index_map)  # the "broadcast" into every (compact) slot
-            else:
-                self.W.copy_(w_global.view(1, -1).expand(self.S, -1))   # the "broadcast" into every slot
+            with PHASES.phase("bcast_local"):
+                if self.index_map is not None:
+                    arena_ops.scatter_in(self.W, w_global, self.index_map)  # the "broadcast" into every (compact) slot
+                else:
+                    self.W.copy_(w_global.view(1, -1).expand(self.S, -1))   # the "broadcast" into every slot
             self.stats.zero_()
             self.loss_sum.zero_()
             if self.first is not None:
@@ -501,10 +517,12 @@ class DeviceClientEngine:
             act[:n_act] = 1
             self.active.copy_(act.to(dev, non_blocking=True))
             self.weights.copy_(w * self.active.float())
-            if self.index_map is not None:
-                arena_ops.accumulate_pseudo_grad_mapped(acc, w_global, self.W, self.weights, self.active, self.index_map)
-            else:
-                arena_ops.accumulate_pseudo_grad(acc, w_global, self.W, self.weights, self.active)
+            with PHASES.phase("gather_local"):
+                if self.index_map is not None:
+                    arena_ops.accumulate_pseudo_grad_mapped(acc, w_global, self.W, self.weights, self.active,
+                                                            self.index_map)
+                else:
+                    arena_ops.accumulate_pseudo_grad(acc, w_global, self.W, self.weights, self.active)
             rec = records[wave_start:wave_start + n_act]
             rec[:, REC_LOSS] = self.loss_sum[:n_act]
             rec[:, REC_SUM:REC_COUNT + 1] = self.stats[:n_act, 0:3]

@@ -263,10 +263,12 @@ class Server:
         if how == "none":
             return
         if how == "flat":
+            from ..utils.timing import PHASES
             buf = worker.weight_buffer() if worker is not None else weights
-            if buf.data_ptr() != weights.data_ptr():
-                buf.copy_(weights)
-            comm.broadcast_weights(buf, src=0)
+            with PHASES.phase("bcast_xgpu"):
+                if buf.data_ptr() != weights.data_ptr():
+                    buf.copy_(weights)
+                comm.broadcast_weights(buf, src=0)
             if worker is not None:
                 worker.weights_updated()
         else:
@@ -316,10 +318,12 @@ def _finish_deferred(comm, worker, local, n_clients, assign=None, cost_of=None):
         wsum = torch.tensor([float(sum((o.get("pl") or {}).get("weight", 0.0) for o in local))], device=acc.device)
     # Σ weight first: with the symmetric-memory transport the server's stream is [barrier A, update kernel, barrier B]
     # and the update kernel needs the total, so the (NCCL) all-reduce must precede barrier A on every rank.
-    comm.all_reduce_(wsum)
-    comm.reduce_accumulators(acc, dst=0)
-    if comm.rank != 0 and comm.kind != "symm":
-        acc.zero_()
+    from ..utils.timing import PHASES
+    with PHASES.phase("gather_xgpu"):
+        comm.all_reduce_(wsum)
+        comm.reduce_accumulators(acc, dst=0)
+        if comm.rank != 0 and comm.kind != "symm":
+            acc.zero_()
 
     def resolve():
         outs = local.resolve() if isinstance(local, DeferredRound) else list(local)
@@ -531,6 +535,9 @@ class Worker:
     def apply_options(self, options):
         if "resident" in options and self.engine is not None:
             self.engine.set_resident(bool(options["resident"]))
+        if "phases" in options:                       # bench.py: per-phase device timers (exposed comm per round)
+            from ..utils.timing import PHASES
+            PHASES.enable(bool(options["phases"]))
 
     def sync_region_ms(self, first, second):
         """Device time between this rank's ``first``-th and ``second``-th ``sync_nodes`` (CUDA events)."""

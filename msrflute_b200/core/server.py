@@ -484,12 +484,14 @@ class OptimizationServer(federated.Server):
         accs = comm.peer_accumulators(worker.accumulator()) if hasattr(comm, "peer_accumulators") \
             else [worker.accumulator()]
         bcast = comm.peer_weight_buffers(worker.weight_buffer()) if hasattr(comm, "peer_weight_buffers") else None
-        ok = self.worker_trainer.fused_update(accs, wsum, noise_scale=noise_scale, seed=seed, bcast=bcast,
-                                              stats_out=stats_out)
+        from ..utils.timing import PHASES
+        with PHASES.phase("update_bcast"):
+            ok = self.worker_trainer.fused_update(accs, wsum, noise_scale=noise_scale, seed=seed, bcast=bcast,
+                                                  stats_out=stats_out)
+            if ok and hasattr(comm, "round_done"):
+                comm.round_done(worker.accumulator())
         if not ok:
             return False
-        if hasattr(comm, "round_done"):
-            comm.round_done(worker.accumulator())
         if bcast is not None and self.server_trainer is None and not self.fall_back_to_best_model:
             self._weights_in_sync = True
         self.strategy.client_weights, self.strategy.client_parameters_stack = [], []

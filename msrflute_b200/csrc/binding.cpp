@@ -62,6 +62,7 @@ std::vector<at::Tensor> softmax_ce(at::Tensor logits, at::Tensor target, double 
 at::Tensor cosine_stats(at::Tensor a, at::Tensor b);
 std::vector<at::Tensor> max_pool2d_fwd(at::Tensor x, int64_t k, int64_t stride, int64_t pad);
 at::Tensor max_pool2d_bwd(at::Tensor dy, at::Tensor arg, int64_t H, int64_t W, int64_t k, int64_t stride, int64_t pad);
+void bind_slotnet(pybind11::module_& m);
 }  // namespace flute
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -100,5 +101,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gru_cell_bwd", &flute::gru_cell_bwd);
   m.def("lstm_cell_fwd", &flute::lstm_cell_fwd);
   m.def("lstm_cell_bwd", &flute::lstm_cell_bwd);
+  flute::bind_slotnet(m);
 
 }

@@ -85,3 +85,47 @@ class TraceWindow:
             self._prof.__exit__(None, None, None)
             self._prof.export_chrome_trace(self.path)
             self._prof, self.path = None, None
+
+
+class PhaseTimer:
+    """Device time per named phase of a round (``bench.py``: the BASELINE metric asks for the *exposed* — not overlapped
+    with client compute — broadcast + gather time per round).  ``with PHASES.phase("gather"):`` brackets the enqueued
+    work with two CUDA events on the current stream; nothing is synchronised until :meth:`totals`.  Disabled (zero
+    cost) unless ``enable()`` was called.  Everything of a round runs on one stream, so a phase's event-to-event time
+    IS its exposed time."""
+
+    def __init__(self):
+        self.enabled = False
+        self._spans = []            # (name, start_event, end_event)
+
+    def enable(self, on=True):
+        self.enabled = bool(on) and torch.cuda.is_available()
+        self._spans = []
+
+    @contextlib.contextmanager
+    def phase(self, name: str):
+        if not self.enabled:
+            yield
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        try:
+            yield
+        finally:
+            b.record()
+            self._spans.append((name, a, b))
+
+    def totals(self, reset=True):
+        """{phase: total device ms} of every span recorded so far (synchronises)."""
+        if not self._spans:
+            return {}
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self._spans:
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        if reset:
+            self._spans = []
+        return out
+
+
+PHASES = PhaseTimer()

@@ -159,22 +159,59 @@ def test_group_norm_fwd_bwd(shape, cpg, per_group, dtype, fuse):
         assert torch.allclose(a, e, **tol), (a - e).abs().max()
 
 
-@pytest.mark.parametrize("conv_impl", ["fma", "auto"])
-def test_engine_round_matches_generic_path(conv_impl):
+@pytest.mark.parametrize("path", ["fma", "tcgen05-r1", "slotnet"])
+def test_engine_round_matches_generic_path(path, monkeypatch):
     """One FedAvg round through the device engine (graphs, slots, fused accumulate) == the generic per-client path.
-    ``fma``: exact-fp32 convolutions, tight tolerance.  ``auto``: tcgen05 tf32 convolutions (cuDNN's default precision
-    too); GroupNorm over 2-channel groups on 1x1 feature maps is a sign function of a difference, so 1e-3 operand
-    rounding is amplified ~1e4x in this configuration — only a sanity bound is asserted here, the tf32 kernels are
-    checked against fp32 with tight bounds in ``test_slot_conv_matches_conv2d`` and on a well-conditioned ResNet in
-    ``test_slot_batched_resnet_matches_per_client_models[auto]``."""
+    ``fma``: the round-1 slot executor with exact-fp32 convolutions, tight tolerance.  ``tcgen05-r1`` / ``slotnet``: tf32
+    tensor-core convolutions (cuDNN's default precision too); GroupNorm over 2-channel groups on 1x1 feature maps is a
+    sign function of a difference, so 1e-3 operand rounding is amplified ~1e4x in this configuration — only a sanity
+    bound is asserted here; the tf32 kernels are checked against fp32 with tight bounds in
+    ``test_slotnet_gemm_gpu.py`` / ``test_slot_conv_matches_conv2d`` and the training trajectory in
+    ``test_flagship_tf32_trajectory_tracks_fp32``."""
     import bench
-    from msrflute_b200.core import client as client_mod
     from msrflute_b200.ops import slot_ops
-    slot_ops.set_conv_impl(conv_impl)
+    monkeypatch.setenv("FLUTE_SLOTNET", "1" if path == "slotnet" else "0")
+    slot_ops.set_conv_impl("fma" if path == "fma" else "auto")
     try:
-        _engine_round_check(bench, 0.02 if conv_impl == "fma" else 0.5)
+        _engine_round_check(bench, 0.02 if path == "fma" else 0.5)
     finally:
         slot_ops.set_conv_impl("auto")
+
+
+def _loss_trajectory(monkeypatch, slotnet, impl, rounds):
+    import bench
+    from msrflute_b200.ops import slot_ops
+    monkeypatch.setenv("FLUTE_SLOTNET", "1" if slotnet else "0")
+    slot_ops.set_conv_impl(impl)
+    torch.manual_seed(1234)
+    job = bench.build_flagship(n_clients_per_round=4, users=8, norm="gn")
+    import random
+    random.seed(99)
+    torch.manual_seed(99)
+    try:
+        return [job.run_round() for _ in range(rounds)]
+    finally:
+        job.close()
+        slot_ops.set_conv_impl("auto")
+
+
+def test_flagship_tf32_trajectory_tracks_fp32(monkeypatch):
+    """The benchmarked numerics: 10 rounds of the flagship config (GroupNorm 2 ch/group down to 1x1 maps) with the tf32
+    SlotNet executor track the exact-fp32 executor's training-loss trajectory.  Same seeds => same clients and the
+    same shuffles; individual gradients differ (see above) but the optimisation must not."""
+    ref = _loss_trajectory(monkeypatch, slotnet=False, impl="fma", rounds=10)
+    got = _loss_trajectory(monkeypatch, slotnet=True, impl="auto", rounds=10)
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "trajectory_tf32_vs_fp32.txt"), "w") as f:
+        f.write("round fp32_exact tf32_slotnet rel_diff\n")
+        for i, (a, b) in enumerate(zip(ref, got)):
+            f.write("{} {:.5f} {:.5f} {:.4f}\n".format(i, a, b, abs(a - b) / abs(a)))
+    assert all(math.isfinite(v) for v in got)
+    assert abs(got[0] - ref[0]) / ref[0] < 0.01, (ref[0], got[0])          # same weights, first round: ~tf32 noise
+    for a, b in zip(ref, got):
+        assert abs(a - b) / a < 0.08, (ref, got)
+    assert min(got[5:]) < got[0] and min(ref[5:]) < ref[0], (ref, got)
 
 
 def _engine_round_check(bench, tol):
