@@ -210,6 +210,12 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) ran while the
+  // previous kernel of the chain was still executing.  Wait for it to complete (its writes are visible afterwards),
+  // THEN let the next kernel start its own prologue — releasing only after the wait means at most two kernels of the
+  // chain are ever co-resident, and every CTA of this grid is already resident when the successor's CTAs arrive.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // =============================================================================================== TMA producer
@@ -934,13 +940,14 @@ class Program {
     op.grid = dim3(row_tiles_total, (g.N + g.TN - 1) / g.TN, g.S);
     op.side = I("side", 0);
     {
-      // Pipeline depth = shared-memory budget / stage size.  These launches are bound by TMA latency (weights stream from
-      // HBM): bytes in flight per SM is what buys bandwidth.  Main-chain launches that fit one CTA per SM take ~160 KB,
-      // grids above 148 CTAs take ~100 KB (two CTAs per SM), weight-gradient launches on the side stream ~64 KB so
-      // they can co-reside with the main chain.
+      // Pipeline depth = shared-memory budget / stage size.  Measured: the K loop is bound by the TMA unit's row rate
+      // (~4 cycles per 128-byte row), not by latency, so 3-4 stages are enough; the budget is kept small instead so that
+      // an SM can hold a CTA of kernel N, the prologue of kernel N+1 (programmatic dependent launch) and a
+      // weight-gradient CTA from the side stream at the same time (84 + 84 + 56 KB).
       const int stage_bytes = A_BYTES + g.TN * 128;
       const long long ctas = static_cast<long long>(op.grid.x) * op.grid.y * op.grid.z;
-      const int budget = I("smem_budget", op.side ? 64 * 1024 : (ctas > 148 ? 100 * 1024 : 160 * 1024));
+      (void)ctas;
+      const int budget = I("smem_budget", op.side ? 56 * 1024 : 84 * 1024);
       g.stages = std::max(2, std::min(kMaxStages, budget / stage_bytes));
       op.smem = g.stages * stage_bytes + SCRATCH_BYTES + (2 * kMaxStages + 2) * 8 + 1024;
     }
@@ -1075,12 +1082,7 @@ class Program {
       }
       switch (op.kind) {
         case 0:
-          switch (op.g.epi) {
-            case E_STORE: sn_gemm_kernel<E_STORE><<<op.grid, kThreads, op.smem, stream>>>(op.g); break;
-            case E_GNFWD: sn_gemm_kernel<E_GNFWD><<<op.grid, kThreads, op.smem, stream>>>(op.g); break;
-            case E_GNBWD: sn_gemm_kernel<E_GNBWD><<<op.grid, kThreads, op.smem, stream>>>(op.g); break;
-            default: sn_gemm_kernel<E_WGRAD><<<op.grid, kThreads, op.smem, stream>>>(op.g); break;
-          }
+          launch_gemm(op, stream);
           break;
         case 1: {
           const long long total = static_cast<long long>(op.N) * 256 * 40;
@@ -1120,6 +1122,31 @@ class Program {
   }
 
   int64_t num_ops() const { return static_cast<int64_t>(ops_.size()); }
+  void set_pdl(bool on) { use_pdl_ = on; }
+
+ private:
+  void launch_gemm(const Op& op, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = op.grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = static_cast<size_t>(op.smem);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = use_pdl_ ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    switch (op.g.epi) {
+      case E_STORE: e = cudaLaunchKernelEx(&cfg, sn_gemm_kernel<E_STORE>, op.g); break;
+      case E_GNFWD: e = cudaLaunchKernelEx(&cfg, sn_gemm_kernel<E_GNFWD>, op.g); break;
+      case E_GNBWD: e = cudaLaunchKernelEx(&cfg, sn_gemm_kernel<E_GNBWD>, op.g); break;
+      default: e = cudaLaunchKernelEx(&cfg, sn_gemm_kernel<E_WGRAD>, op.g); break;
+    }
+    FLUTE_CUDA_CHECK(e);
+  }
+
+ public:
 
  private:
   std::vector<CUtensorMap> host_maps_;
@@ -1128,6 +1155,7 @@ class Program {
   torch::Tensor maps_dev_;
   bool finalized_ = false;
   bool use_side_ = false;
+  bool use_pdl_ = true;
   cudaStream_t side_stream_ = nullptr;
   cudaEvent_t join_event_ = nullptr;
   std::vector<cudaEvent_t> fork_events_;
@@ -1149,6 +1177,7 @@ void bind_slotnet(py::module_& m) {
       .def("finalize", &sn::Program::finalize)
       .def("run", &sn::Program::run, py::arg("begin") = 0, py::arg("end") = -1)
       .def("set_side_stream", &sn::Program::set_side_stream)
+      .def("set_pdl", &sn::Program::set_pdl)
       .def("num_ops", &sn::Program::num_ops);
 }
 

@@ -36,10 +36,11 @@ def _live_taps(Hi, Wi, KH, KW, stride, pad):
     return [(kh, kw) for kh in rows for kw in cols]
 
 
-def _pick_tn(n, other_tiles=10 ** 9, target=128):
-    """N-tile width.  These layers are launch- and weight-bandwidth-bound, not MMA-bound: the weight (B operand)
-    traffic does not depend on the tile width, so prefer the widest tile that still gives ~one CTA per SM
-    (``other_tiles`` = row tiles x slots) and fall back to narrow tiles when the layer has few rows."""
+def _pick_tn(n, other_tiles=10 ** 9, target=96):
+    """N-tile width.  These layers are bound by the per-SM TMA row rate and per-CTA latency, not by the MMA: the weight
+    (B operand) traffic does not depend on the tile width while the A operand is re-read once per N tile.  Prefer the
+    widest tile that still gives ~one CTA per SM (``other_tiles`` = row tiles x slots; two CTAs on one SM share its TMA
+    unit, so more than 148 CTAs buys nothing) and fall back to narrow tiles when the layer has few rows."""
     cands = [t for t in (256, 128, 64, 32) if t <= max(32, n)]
     for t in cands:
         if other_tiles * math.ceil(n / t) >= target:
@@ -372,6 +373,7 @@ class SlotNetResNet(SlotProgramBuilder):
         self.prog.finalize()
         import os as _os
         self.prog.set_side_stream(_os.environ.get("FLUTE_SLOTNET_SIDE", "1") == "1")
+        self.prog.set_pdl(_os.environ.get("FLUTE_SLOTNET_PDL", "1") == "1")
         self.n_ops = self.prog.num_ops()
 
     def _gn(self, name):

@@ -99,8 +99,11 @@ class PhaseTimer:
         self._spans = []            # (name, start_event, end_event)
 
     def enable(self, on=True):
-        self.enabled = bool(on) and torch.cuda.is_available()
-        self._spans = []
+        """Switching ON starts a fresh measurement; switching OFF keeps the recorded spans for :meth:`totals`."""
+        on = bool(on) and torch.cuda.is_available()
+        if on:
+            self._spans = []
+        self.enabled = on
 
     @contextlib.contextmanager
     def phase(self, name: str):
