@@ -45,6 +45,63 @@ def seed_data(root):
                      offsets=np.arange(users + 1) * n, f_image=imgs, f_label=labels.reshape(-1).astype(np.int64))
 
 
+def seed_femnist(root):
+    """FedEMNIST-shaped files for the reference's own reader (``./data/femnist/fed_emnist_*.h5`` through the h5py shim):
+    3400 train users x ~100 samples, 28x28 float pixels, 62 classes — the shape ``experiments/cv_cnn_femnist`` of this
+    repo synthesises for its own arm."""
+    import numpy as np
+    d = os.path.join(root, "data", "femnist")
+    os.makedirs(d, exist_ok=True)
+    tar = os.path.join(root, "data", "fed_emnist.tar.bz2")
+    if not os.path.exists(tar):
+        open(tar, "wb").close()
+    for fname, users, mean, seed in (("fed_emnist_train.h5", 3400, 100, 3), ("fed_emnist_test.h5", 340, 40, 4)):
+        path = os.path.join(d, fname)
+        if os.path.exists(path):
+            continue
+        rng = np.random.default_rng(seed)
+        protos = np.random.default_rng(1234).random((62, 28, 28)).astype(np.float32)
+        sizes = np.maximum(2, rng.poisson(mean, size=users))
+        off = np.concatenate([[0], np.cumsum(sizes)])
+        labels = rng.integers(0, 62, size=off[-1])
+        px = (0.5 * protos[labels] + 0.5 * rng.random((off[-1], 28, 28), dtype=np.float32)).astype(np.float32)
+        with open(path, "wb") as f:
+            np.savez(f, users=np.array(["f{:05d}".format(u) for u in range(users)]), offsets=off, f_pixels=px,
+                     f_label=labels.astype(np.int64))
+
+
+def seed_shakespeare(root):
+    """Shakespeare-shaped files: 715 train users whose ``snippets`` tokenise (by the reference's own ``preprocess``)
+    into ~50 sequences of 80 characters each."""
+    import numpy as np
+    d = os.path.join(root, "data", "fed_shakespeare")
+    os.makedirs(d, exist_ok=True)
+    tar = os.path.join(root, "data", "shakespeare.tar.bz2")
+    if not os.path.exists(tar):
+        open(tar, "wb").close()
+    vocab = list("dhlptx@DHLPTX $(,048cgkoswCGKOSW[_#'/37;?bfjnrvzBFJNRVZ&*.26:aeimquyAEIMQUY]!%)-159")
+    for fname, users, mean, seed in (("shakespeare_train.h5", 715, 50, 7), ("shakespeare_test.h5", 100, 30, 8)):
+        path = os.path.join(d, fname)
+        if os.path.exists(path):
+            continue
+        rng = np.random.default_rng(seed)
+        sizes = np.maximum(2, rng.poisson(mean, size=users))
+        snippets = []
+        for n in sizes:
+            chars = rng.integers(0, len(vocab), size=int(n) * 81 - 2)       # + <bos>, <eos> = n full sequences
+            snippets.append("".join(vocab[c] for c in chars).encode("utf8"))
+        arr = np.empty(len(snippets), dtype=object)
+        arr[:] = snippets
+        with open(path, "wb") as f:
+            np.savez(f, users=np.array(["s{:05d}".format(u) for u in range(users)]), offsets=np.arange(users + 1),
+                     f_snippets=arr)
+
+
+SEEDERS = {"cv_resnet_fedcifar100": ("fed_cifar100", "fed_cifar100_test.h5"),
+           "cv_cnn_femnist": ("femnist", "fed_emnist_test.h5"),
+           "nlp_rnn_fedshakespeare": ("fed_shakespeare", "shakespeare_test.h5")}
+
+
 def main():
     args = parse_args()
     if args.clients_per_round is None:
@@ -68,10 +125,18 @@ def main():
         if rank == 0:
             emit({"impl": "reference", "unavailable": "no CUDA device: the reference's NCCL path needs GPUs"})
         return
+    if args.task not in SEEDERS:
+        if rank == 0:
+            emit({"impl": "reference", "metric": TASKS[args.task]["metric"],
+                  "unavailable": "no offline data seeder for the reference's {} reader (needs HF model/tokenizer "
+                                 "downloads)".format(args.task)})
+        return
     if rank == 0:
-        seed_data(REF)
+        {"cv_resnet_fedcifar100": seed_data, "cv_cnn_femnist": seed_femnist,
+         "nlp_rnn_fedshakespeare": seed_shakespeare}[args.task](REF)
     else:
-        while not os.path.exists(os.path.join(REF, "data", "fed_cifar100", "fed_cifar100_test.h5")):
+        sub, last = SEEDERS[args.task]
+        while not os.path.exists(os.path.join(REF, "data", sub, last)):
             time.sleep(0.5)
         time.sleep(1.0)
 
@@ -84,6 +149,11 @@ def main():
     sc["num_clients_per_iteration"] = args.clients_per_round
     sc["val_freq"], sc["rec_freq"] = 10 ** 9, 10 ** 9     # rounds only, like our arm: no eval inside the timed region
     sc["initial_val"], sc["initial_rec"] = False, False
+    for section, upd in (TASKS[args.task].get("overrides") or {}).items():     # same algorithmic config as our arm
+        tgt, keys = cfg, section.split(".")
+        for k in keys[:-1]:
+            tgt = tgt.setdefault(k, {})
+        tgt[keys[-1]] = upd
     out_dir = os.path.join("/tmp", "flute_ref_bench_{}".format(os.environ.get("MASTER_PORT", "0")))
     os.makedirs(out_dir, exist_ok=True)
     cfg_path = os.path.join(out_dir, "bench_{}.yaml".format(args.task))
@@ -129,6 +199,25 @@ def main():
     wall_ms = (w1 - w0) * 1e3
     ms = e0.elapsed_time(e1) if e0 is not None else wall_ms      # CUDA events on rank 0 (it waits for every worker)
     value = args.steps / (ms / 1e3)
+    spec = TASKS[args.task]
+    flagship = args.task == "cv_resnet_fedcifar100"
+    if not flagship:
+        emit({"impl": "reference", "metric": spec["metric"], "value": value, "unit": "rounds/s", "n_gpus": world,
+              "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+              "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+              "vs_baseline": (value / BASELINE_PUBLISHED[args.task]) if BASELINE_PUBLISHED.get(args.task) else None,
+              "dtype": "fp32", "data": spec["data"], "clocks": state["clocks"],
+              "e2e": {"value": args.steps / (wall_ms / 1e3), "unit": "rounds/s", "h2d_bytes_per_step": None,
+                      "d2h_bytes_per_step": None,
+                      "note": "wall clock between the reference's own per-round log calls (it moves every mini-batch "
+                              "host->device and every gradient device->host itself)"},
+              "gpu_launches": None,
+              "config": dict(spec["config"], clients_per_round=args.clients_per_round,
+                             parallelism="server+{}workers".format(max(world - 1, 1)) if world > 1
+                             else "single-gpu thread path",
+                             note="reference config.yaml as shipped (strategy/quantization overrides of our arm "
+                                  "are applied where the reference supports them)")})
+        return
     emit({"impl": "reference", "metric": HEADLINE_METRIC, "value": value, "unit": "rounds/s", "n_gpus": world,
           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
           "higher_is_better": True, "scaling": "strong", "vs_baseline": value / BASELINE_PUBLISHED_ROUNDS_PER_SEC,

@@ -276,6 +276,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
         "median_ms_per_round": med, "rounds_per_s_at_median": (1e3 / med) if med else None,
         "round_ms_min_max": [round(min(per_round), 3), round(max(per_round), 3)] if per_round else None,
+        "slowest_rounds": sorted(([i, round(v, 2)] for i, v in enumerate(per_round)), key=lambda t: -t[1])[:5],
         "setup_rounds": setup_rounds,
         "higher_is_better": True, "scaling": "strong",
         "vs_baseline": (value / BASELINE_PUBLISHED[args.task]) if BASELINE_PUBLISHED.get(args.task) else None,

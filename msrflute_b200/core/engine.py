@@ -121,12 +121,17 @@ class DeviceClientEngine:
     # ------------------------------------------------------------------ capability
     def supports(self, cfg) -> bool:
         cc, sc = cfg["client_config"], cfg["server_config"]
-        if str(cfg["strategy"]).lower() not in ("fedavg", "dga"):
+        strategy = str(cfg["strategy"]).lower()
+        if strategy not in ("fedavg", "dga", "fedprox"):
             return False
         if cc["optimizer_config"].get("type") != "sgd":
             return False
         dp = cfg.get("dp_config", None) or {}
-        if dp.get("enable_local_dp", False) or cc.get("quant_thresh", None) is not None:
+        # local DP (DGA): clip / normalise + Gaussian noise are fused into the gather; FedProx: closed-form proximal
+        # gradient in the fused step.  Gradient quantization still takes the generic per-client path.
+        if cc.get("quant_thresh", None) is not None:
+            return False
+        if dp.get("enable_local_dp", False) and strategy != "dga":
             return False
         pm = cfg.get("privacy_metrics_config", None) or {}
         if pm.get("apply_metrics", False) or sc.get("type", "model_optimization") == "personalization":
@@ -163,6 +168,33 @@ class DeviceClientEngine:
             self.index_map = None
         self.W = torch.zeros(self.S, P, device=dev)
         self.G = torch.zeros(self.S, P, device=dev)
+        # slot-layout rows: the round's global weights and the round's accumulator (the permutation to / from the
+        # global arena layout is paid once per round on these single rows, see csrc/gather_kernels.cu)
+        self.wg_slot = torch.zeros(P, device=dev) if self.index_map is not None else None
+        self.acc_slot = torch.zeros(P, device=dev) if self.index_map is not None else None
+        self.pg_norm2 = torch.zeros(self.S, device=dev)
+        self._dead_idx = None
+        self._w_ref = None
+        strategy = str(self.config["strategy"]).lower()
+        cc = self.config["client_config"]
+        self.prox_mult = self.prox_loss = None
+        if strategy == "fedprox":
+            mu = float(cc.get("mu", 0.001))
+            ref_mult = bool(cc.get("fedprox_reference_multiplicity", True))
+            lay = self.layout
+            n_t = len(lay.sizes)
+            glob = torch.zeros(lay.padded_numel)
+            for i, (o, k) in enumerate(zip(lay.offsets, lay.sizes)):
+                glob[o:o + k] = mu * ((n_t - i) if ref_mult else 1.0)     # the reference counts tensor i (P - i) times
+            if self.index_map is not None:
+                m = self.index_map.long().cpu()
+                row = torch.where(m >= 0, glob[m.clamp(min=0)], torch.zeros(()))
+            else:
+                row = glob
+            self.prox_mult = row.to(dev).contiguous()
+            self.prox_loss = torch.zeros(self.S, device=dev)
+        self.dp = dict(self.config.get("dp_config", None) or {})
+        self.local_dp = bool(self.dp.get("enable_local_dp", False)) and strategy == "dga"
         self.slots: List[_Slot] = []
         for s in range(self.S if self.slot_plan is None else 0):
             m = copy.deepcopy(base)
@@ -305,10 +337,15 @@ class DeviceClientEngine:
         arena_ops.fused_client_step(
             self.W[s:s + 1], self.G[s:s + 1], self.hyper[s:s + 1], self.stats[s:s + 1],
             self.M[s:s + 1] if self.M is not None else None, n_logical=self.layout.numel, nesterov=self.nesterov,
-            dampening=self.dampening, zero_grad=True, first_step=self.first[s:s + 1] if self.first is not None else None)
+            dampening=self.dampening, zero_grad=True, first_step=self.first[s:s + 1] if self.first is not None else None,
+            prox_ref=self._prox_ref(), prox_mult=self.prox_mult,
+            prox_loss=self.prox_loss[s:s + 1] if self.prox_loss is not None else None)
         if self.first is not None:
             self.first[s:s + 1].zero_()
         self.loss_sum[s:s + 1] += loss.detach().float().reshape(1)
+        if self.prox_loss is not None:
+            self.loss_sum[s:s + 1] += self.prox_loss[s:s + 1]
+            self.prox_loss[s:s + 1].zero_()
 
     def _run_step(self, slot: _Slot, idx):
         key = int(idx.numel())
@@ -353,10 +390,14 @@ class DeviceClientEngine:
                 losses.sum().backward()                # weight grads are accumulated into self.G by the kernels
             arena_ops.fused_client_step(self.W, self.G, self.hyper, self.stats, self.M, n_logical=self.layout.numel,
                                         nesterov=self.nesterov, dampening=self.dampening, zero_grad=True,
-                                        first_step=self.first)
+                                        first_step=self.first, prox_ref=self._prox_ref(), prox_mult=self.prox_mult,
+                                        prox_loss=self.prox_loss)
             if self.first is not None:
                 self.first.zero_()
             self.loss_sum += losses.detach().float()
+            if self.prox_loss is not None:             # the reference's batch loss includes the proximal term
+                self.loss_sum += self.prox_loss
+                self.prox_loss.zero_()
             return
         from torch.func import functional_call, grad_and_value, vmap
 
@@ -367,10 +408,32 @@ class DeviceClientEngine:
         torch._foreach_copy_(self.grad_stack, [grads[n] for n in self.param_names])
         arena_ops.fused_client_step(self.W, self.G, self.hyper, self.stats, self.M, n_logical=self.layout.numel,
                                     nesterov=self.nesterov, dampening=self.dampening, zero_grad=True,
-                                    first_step=self.first)
+                                    first_step=self.first, prox_ref=self._prox_ref(), prox_mult=self.prox_mult,
+                                    prox_loss=self.prox_loss)
         if self.first is not None:
             self.first.zero_()
         self.loss_sum += losses.detach().float()
+        if self.prox_loss is not None:
+            self.loss_sum += self.prox_loss
+            self.prox_loss.zero_()
+
+    def _prox_ref(self):
+        """FedProx anchor = the round's global weights in the slot layout (a static buffer, safe inside CUDA graphs)."""
+        if self.prox_mult is None:
+            return None
+        return self.wg_slot if self.wg_slot is not None else self._w_ref
+
+    def _dead_coords(self):
+        """Global-arena positions of real parameters that no slot stores (elided dead filter taps)."""
+        if self._dead_idx is None:
+            lay = self.layout
+            is_param = torch.zeros(lay.padded_numel, dtype=torch.bool)
+            for o, k in zip(lay.offsets, lay.sizes):
+                is_param[o:o + k] = True
+            m = self.index_map.long().cpu()
+            is_param[m[m >= 0]] = False
+            self._dead_idx = is_param.nonzero().view(-1).to(torch.int32).to(self.device)
+        return self._dead_idx
 
     def _run_wave_step(self, idx2d):
         """``idx2d``: [S, B] global sample rows.  Returns False if this model cannot be vmapped (caller falls back)."""
@@ -441,9 +504,14 @@ class DeviceClientEngine:
             n_act = len(wave)
             with PHASES.phase("bcast_local"):
                 if self.index_map is not None:
-                    arena_ops.scatter_in(self.W, w_global, self.index_map)  # the "broadcast" into every (compact) slot
+                    # the "broadcast" into every (compact) slot: one gather through the layout permutation, S + 1 rows out
+                    arena_ops.slot_gather_bcast(self.W, self.wg_slot, w_global, self.index_map)
                 else:
                     self.W.copy_(w_global.view(1, -1).expand(self.S, -1))   # the "broadcast" into every slot
+                    if self.prox_mult is not None:
+                        if getattr(self, "_w_ref", None) is None:
+                            self._w_ref = torch.empty_like(w_global)
+                        self._w_ref.copy_(w_global)
             self.stats.zero_()
             self.loss_sum.zero_()
             if self.first is not None:
@@ -516,13 +584,42 @@ class DeviceClientEngine:
             act = torch.zeros(self.S, dtype=torch.int32)
             act[:n_act] = 1
             self.active.copy_(act.to(dev, non_blocking=True))
-            self.weights.copy_(w * self.active.float())
+            actf = self.active.float()
+            wg_row = self.wg_slot if self.index_map is not None else w_global
+            acc_row = self.acc_slot if self.index_map is not None else acc
+            sig = seeds = None
             with PHASES.phase("gather_local"):
-                if self.index_map is not None:
-                    arena_ops.accumulate_pseudo_grad_mapped(acc, w_global, self.W, self.weights, self.active,
-                                                            self.index_map)
+                if self.local_dp:
+                    # local DP fused into the gather (ref. extensions/privacy/__init__.py:154-201): per-client norm of the
+                    # pseudo-gradient -> clip (eps < 0) or normalise to max_grad + Gaussian noise; all on the device
+                    dpc = self.dp
+                    C = float(dpc["max_grad"])
+                    norm = arena_ops.slot_pg_sqnorm(self.W, wg_row, self.pg_norm2).sqrt().clamp(min=1e-12)
+                    if float(dpc["eps"]) < 0:
+                        scale = (C / norm).clamp(max=1.0)
+                    else:
+                        from ..extensions.privacy import compute_LDP_noise_std, rng as dp_rng
+                        scaler = float(dpc.get("weight_scaler", 1))
+                        sens = math.sqrt(C ** 2 + (float(dpc["max_weight"]) ** 2 if softmax else 0.0))
+                        sigma = float(compute_LDP_noise_std(float(dpc["eps"]), sens, float(dpc.get("delta", 1e-7))))
+                        scale = C / norm
+                        if softmax:                                    # noisy aggregation weight (add_weight_noise)
+                            noisy = (w * scaler).clamp(max=float(dpc["max_weight"])) + sigma * dp_rng.randn((self.S,), dev)
+                            w = noisy.clamp(min=float(dpc["min_weight"]), max=float(dpc["max_weight"])) / scaler
+                        sig = w * actf * sigma
+                        seeds = torch.tensor([dp_rng.dp_seed(stream=100 + i) for i in range(self.S)],
+                                             dtype=torch.int64).to(dev, non_blocking=True)
+                    self.weights.copy_(w * actf)
+                    coef = self.weights * scale
                 else:
-                    arena_ops.accumulate_pseudo_grad(acc, w_global, self.W, self.weights, self.active)
+                    self.weights.copy_(w * actf)
+                    coef = self.weights
+                arena_ops.slot_gather_fused(acc_row, self.W, wg_row, coef, sig, seeds)
+                if self.index_map is not None:
+                    arena_ops.slot_scatter_acc(acc, self.acc_slot, self.index_map)
+                    if sig is not None:
+                        from ..extensions.privacy import rng as dp_rng
+                        arena_ops.dead_coord_noise(acc, self._dead_coords(), (sig * sig).sum(), dp_rng.dp_seed(stream=99))
             rec = records[wave_start:wave_start + n_act]
             rec[:, REC_LOSS] = self.loss_sum[:n_act]
             rec[:, REC_SUM:REC_COUNT + 1] = self.stats[:n_act, 0:3]

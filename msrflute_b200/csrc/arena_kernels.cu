@@ -30,9 +30,47 @@ static inline int blocks_for(int64_t n_vec4) {
 
 // ---------------------------------------------------------------------------------------------------- reduce
 // partial[s][b] = (sum g, sum g^2) over block b's share of row s
+// FedProx: the proximal term (mu/2)||w - w_global||^2 is part of the client loss in the reference
+// (core/trainer.py:463-467), i.e. its gradient pmult[j] * (w - w_ref) joins the back-propagated gradient BEFORE clipping
+// and the gradient statistics.  Closed form, folded into both passes (pmult carries mu times the reference's per-tensor
+// multiplicity, see Trainer.fedprox_multiplicity); no autograd graph of P norms.
+__device__ __forceinline__ float4 prox_grad(float4 g, const float4 w, const float4 r, const float4 m) {
+  g.x = fmaf(m.x, w.x - r.x, g.x); g.y = fmaf(m.y, w.y - r.y, g.y);
+  g.z = fmaf(m.z, w.z - r.z, g.z); g.w = fmaf(m.w, w.w - r.w, g.w);
+  return g;
+}
+
 __global__ void __launch_bounds__(kThreads) row_reduce_kernel(const float* __restrict__ g, int64_t P,
-                                                              float2* __restrict__ partial) {
+                                                              float2* __restrict__ partial,
+                                                              const float* __restrict__ w = nullptr,
+                                                              const float* __restrict__ wref = nullptr,
+                                                              const float* __restrict__ pmult = nullptr,
+                                                              float* __restrict__ prox_loss = nullptr) {
   const int s = blockIdx.y;
+  if (pmult != nullptr) {
+    // FedProx variant (one extra read of w and of the two shared rows)
+    const float4* gv = reinterpret_cast<const float4*>(g + static_cast<int64_t>(s) * P);
+    const float4* wv = reinterpret_cast<const float4*>(w + static_cast<int64_t>(s) * P);
+    const float4* rv = reinterpret_cast<const float4*>(wref);
+    const float4* mv = reinterpret_cast<const float4*>(pmult);
+    const int64_t n4 = P >> 2, stride = static_cast<int64_t>(gridDim.x) * kThreads;
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n4; i += stride) {
+      const float4 ww = ld_na(wv + i), rr = __ldg(rv + i), mm = __ldg(mv + i);
+      const float4 v = prox_grad(ld_na(gv + i), ww, rr, mm);
+      a += (v.x + v.y) + (v.z + v.w);
+      b += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      const float dx = ww.x - rr.x, dy = ww.y - rr.y, dz = ww.z - rr.z, dw = ww.w - rr.w;
+      c += 0.5f * ((mm.x * dx * dx + mm.y * dy * dy) + (mm.z * dz * dz + mm.w * dw * dw));   // the term's loss value
+    }
+    const float2 r = block_sum2(a, b);
+    if (threadIdx.x == 0) partial[static_cast<int64_t>(s) * gridDim.x + blockIdx.x] = r;
+    if (prox_loss != nullptr) {
+      const float2 r2 = block_sum2(c, 0.f);
+      if (threadIdx.x == 0) atomicAdd(prox_loss + s, r2.x);
+    }
+    return;
+  }
   const float4* gv = reinterpret_cast<const float4*>(g + static_cast<int64_t>(s) * P);
   const int64_t n4 = P >> 2;
   float a = 0.f, b = 0.f;
@@ -74,7 +112,8 @@ __global__ void __launch_bounds__(kThreads)
 row_update_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ mom, int64_t P,
                   const float2* __restrict__ partial, int nb_reduce, const float* __restrict__ hyper,
                   float* __restrict__ stats, const int* __restrict__ first_step, float n_logical, bool nesterov,
-                  float dampening, bool zero_grad) {
+                  float dampening, bool zero_grad, const float* __restrict__ wref = nullptr,
+                  const float* __restrict__ pmult = nullptr) {
   const int s = blockIdx.y;
   const float2 tot = fold_partials(partial + static_cast<int64_t>(s) * nb_reduce, nb_reduce);
   const float lr = hyper[s * 4 + 0], max_norm = hyper[s * 4 + 1], wd = hyper[s * 4 + 2], mu = hyper[s * 4 + 3];
@@ -101,6 +140,8 @@ row_update_kernel(float* __restrict__ w, float* __restrict__ g, float* __restric
       continue;
     }
     float4 ww = ld_na(wv + i);
+    if (pmult != nullptr)
+      gg = prox_grad(gg, ww, __ldg(reinterpret_cast<const float4*>(wref) + i), __ldg(reinterpret_cast<const float4*>(pmult) + i));
     float4 d = make_float4(fmaf(coef, gg.x, wd * ww.x), fmaf(coef, gg.y, wd * ww.y), fmaf(coef, gg.z, wd * ww.z),
                            fmaf(coef, gg.w, wd * ww.w));
     if (kMomentum) {
@@ -129,7 +170,8 @@ static void check_rows(const torch::Tensor& t, const char* name) {
 
 void fused_client_step(torch::Tensor w, torch::Tensor g, torch::Tensor hyper, torch::Tensor stats,
                        c10::optional<torch::Tensor> mom, c10::optional<torch::Tensor> first_step, int64_t n_logical,
-                       bool nesterov, double dampening, bool zero_grad) {
+                       bool nesterov, double dampening, bool zero_grad, c10::optional<torch::Tensor> prox_ref,
+                       c10::optional<torch::Tensor> prox_mult, c10::optional<torch::Tensor> prox_loss) {
   check_rows(w, "w");
   check_rows(g, "g");
   TORCH_CHECK(w.sizes() == g.sizes(), "w/g shape mismatch");
@@ -140,20 +182,31 @@ void fused_client_step(torch::Tensor w, torch::Tensor g, torch::Tensor hyper, to
   auto stream = at::cuda::getCurrentCUDAStream();
   const int nb = blocks_for(P >> 2);
   auto partial = torch::empty({S, nb, 2}, w.options());
+  const float* pref = nullptr;
+  const float* pmul = nullptr;
+  if (prox_ref.has_value() && prox_mult.has_value()) {
+    TORCH_CHECK(prox_ref->numel() == P && prox_mult->numel() == P && prox_ref->scalar_type() == torch::kFloat32 &&
+                prox_mult->scalar_type() == torch::kFloat32 && prox_ref->is_cuda() && prox_mult->is_cuda(),
+                "FedProx: reference weights and per-element multipliers must be fp32 CUDA rows of length P");
+    pref = prox_ref->data_ptr<float>();
+    pmul = prox_mult->data_ptr<float>();
+  }
   row_reduce_kernel<<<dim3(nb, S), kThreads, 0, stream>>>(g.data_ptr<float>(), P,
-                                                         reinterpret_cast<float2*>(partial.data_ptr<float>()));
+                                                         reinterpret_cast<float2*>(partial.data_ptr<float>()),
+                                                         w.data_ptr<float>(), pref, pmul,
+                                                         prox_loss.has_value() ? prox_loss->data_ptr<float>() : nullptr);
   const int* fs = first_step.has_value() ? first_step->data_ptr<int>() : nullptr;
   if (mom.has_value()) {
     check_rows(*mom, "mom");
     row_update_kernel<true, false><<<dim3(nb, S), kThreads, 0, stream>>>(
         w.data_ptr<float>(), g.data_ptr<float>(), mom->data_ptr<float>(), P,
         reinterpret_cast<const float2*>(partial.data_ptr<float>()), nb, hyper.data_ptr<float>(), stats.data_ptr<float>(),
-        fs, static_cast<float>(n_logical), nesterov, static_cast<float>(dampening), zero_grad);
+        fs, static_cast<float>(n_logical), nesterov, static_cast<float>(dampening), zero_grad, pref, pmul);
   } else {
     row_update_kernel<false, false><<<dim3(nb, S), kThreads, 0, stream>>>(
         w.data_ptr<float>(), g.data_ptr<float>(), nullptr, P, reinterpret_cast<const float2*>(partial.data_ptr<float>()),
         nb, hyper.data_ptr<float>(), stats.data_ptr<float>(), nullptr, static_cast<float>(n_logical), nesterov,
-        static_cast<float>(dampening), zero_grad);
+        static_cast<float>(dampening), zero_grad, pref, pmul);
   }
   FLUTE_CUDA_CHECK(cudaGetLastError());
 }

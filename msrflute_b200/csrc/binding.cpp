@@ -4,7 +4,14 @@
 namespace flute {
 void fused_client_step(torch::Tensor w, torch::Tensor g, torch::Tensor hyper, torch::Tensor stats,
                        c10::optional<torch::Tensor> mom, c10::optional<torch::Tensor> first_step, int64_t n_logical,
-                       bool nesterov, double dampening, bool zero_grad);
+                       bool nesterov, double dampening, bool zero_grad, c10::optional<torch::Tensor> prox_ref,
+                       c10::optional<torch::Tensor> prox_mult, c10::optional<torch::Tensor> prox_loss);
+void slot_gather_bcast(torch::Tensor W, torch::Tensor wg_slot, torch::Tensor wg, torch::Tensor map);
+void slot_pg_sqnorm(torch::Tensor W, torch::Tensor wg_slot, torch::Tensor out);
+void slot_gather_fused(torch::Tensor acc_slot, torch::Tensor W, torch::Tensor wg_slot, torch::Tensor coef,
+                       c10::optional<torch::Tensor> sig, c10::optional<torch::Tensor> seed);
+void slot_scatter_acc(torch::Tensor acc, torch::Tensor acc_slot, torch::Tensor map);
+void dead_coord_noise(torch::Tensor acc, torch::Tensor idx, torch::Tensor sig2_sum, int64_t seed);
 void clip_and_stats(torch::Tensor g, torch::Tensor hyper, torch::Tensor stats, int64_t n_logical);
 void pseudo_grad(torch::Tensor wg, torch::Tensor wl, torch::Tensor out, c10::optional<torch::Tensor> weight,
                  c10::optional<torch::Tensor> stats);
@@ -63,11 +70,26 @@ at::Tensor cosine_stats(at::Tensor a, at::Tensor b);
 std::vector<at::Tensor> max_pool2d_fwd(at::Tensor x, int64_t k, int64_t stride, int64_t pad);
 at::Tensor max_pool2d_bwd(at::Tensor dy, at::Tensor arg, int64_t H, int64_t W, int64_t k, int64_t stride, int64_t pad);
 void bind_slotnet(pybind11::module_& m);
+bool lstm_supported(int64_t H);
+std::vector<torch::Tensor> lstm_layer_fwd(torch::Tensor gx, torch::Tensor whh, c10::optional<torch::Tensor> h0,
+                                          c10::optional<torch::Tensor> c0);
+std::vector<torch::Tensor> lstm_layer_bwd(torch::Tensor dhs, torch::Tensor gates, torch::Tensor cs, torch::Tensor whh,
+                                          c10::optional<torch::Tensor> c0, c10::optional<torch::Tensor> dhT,
+                                          c10::optional<torch::Tensor> dcT);
 }  // namespace flute
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "msrflute_b200 hand-written sm_100a kernels";
-  m.def("fused_client_step", &flute::fused_client_step);
+  m.def("fused_client_step", &flute::fused_client_step, pybind11::arg("w"), pybind11::arg("g"), pybind11::arg("hyper"),
+        pybind11::arg("stats"), pybind11::arg("mom"), pybind11::arg("first_step"), pybind11::arg("n_logical"),
+        pybind11::arg("nesterov"), pybind11::arg("dampening"), pybind11::arg("zero_grad"),
+        pybind11::arg("prox_ref") = pybind11::none(), pybind11::arg("prox_mult") = pybind11::none(),
+        pybind11::arg("prox_loss") = pybind11::none());
+  m.def("slot_gather_bcast", &flute::slot_gather_bcast);
+  m.def("slot_pg_sqnorm", &flute::slot_pg_sqnorm);
+  m.def("slot_gather_fused", &flute::slot_gather_fused);
+  m.def("slot_scatter_acc", &flute::slot_scatter_acc);
+  m.def("dead_coord_noise", &flute::dead_coord_noise);
   m.def("clip_and_stats", &flute::clip_and_stats);
   m.def("pseudo_grad", &flute::pseudo_grad);
   m.def("accumulate_pseudo_grad", &flute::accumulate_pseudo_grad);
@@ -102,5 +124,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lstm_cell_fwd", &flute::lstm_cell_fwd);
   m.def("lstm_cell_bwd", &flute::lstm_cell_bwd);
   flute::bind_slotnet(m);
+  m.def("lstm_supported", &flute::lstm_supported);
+  m.def("lstm_layer_fwd", &flute::lstm_layer_fwd);
+  m.def("lstm_layer_bwd", &flute::lstm_layer_bwd);
 
 }

@@ -99,6 +99,9 @@ struct GemmP {
   int a_lbo, a_sbo, a_kstep, a_layout;
   int b_lbo, b_sbo, b_kstep, b_layout;
   int stages;                // TMA -> MMA ring depth (2..kMaxStages)
+  int nacc;                  // independent TMEM accumulators (1, 2 or 4): UMMA k-step j of a stage accumulates into
+                             // accumulator j % nacc, the epilogue adds them — shortens the dependent-MMA chain
+  int dbg;                   // measurement hooks: bit 0 = skip the MMAs, bit 1 = skip the TMA loads
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -126,6 +129,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
   return d;
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// 32 accumulator columns of this thread's row, summed over the `nacc` independent accumulators (TN columns apart)
+__device__ __forceinline__ void tmem_ld_acc(uint32_t taddr, int TN, int nacc, uint32_t (&v)[32]) {
+  tmem_ld_32x32(taddr, v);
+  for (int a = 1; a < nacc; ++a) {
+    uint32_t w[32];
+    tmem_ld_32x32(taddr + static_cast<uint32_t>(a * TN), w);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+  }
+}
 
 // all-reduce of two 16-value arrays over the NL lanes of an image segment (fully unrolled: these epilogues run with
 // one warp per scheduler, so every avoided instruction is latency off the critical path of the launch)
@@ -205,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
     fence_barrier_init();
   }
   if (warp == 0 && lane < 5) prefetch_tmap(p.maps + lane);
-  if (warp == 1) tmem_alloc(tmem_ptr, static_cast<uint32_t>(p.TN));
+  if (warp == 1) tmem_alloc(tmem_ptr, static_cast<uint32_t>(p.TN * p.nacc));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -235,6 +249,7 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
           int kb0, ky0;
           if (p.kbb > 1) { kb0 = pc * p.kbb; ky0 = 0; }
           else { kb0 = pc / per_img; ky0 = (pc - kb0 * per_img) * p.kbh; }
+          if (p.dbg & 2) { mbar_expect_tx(full_bar + s, 0); continue; }
           mbar_expect_tx(full_bar + s, tx);
           for (int i = 0; i < 4; ++i) {
             const int r = rb * TM + 32 * i;
@@ -257,6 +272,7 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
             mbar_wait(empty_bar + s, ((it / kStages) & 1) ^ 1);
             uint8_t* sa = smem + s * stage_bytes;
             uint8_t* sb = sa + A_BYTES;
+            if (p.dbg & 2) { mbar_expect_tx(full_bar + s, 0); continue; }
             mbar_expect_tx(full_bar + s, tx);
             tma_load_5d(sa, mapA, full_bar + s, c0, cx, cy, b0, slot);
             if (p.mode == FPROP) {
@@ -282,9 +298,14 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
         const uint64_t adesc = make_desc(a_addr, p.a_lbo, p.a_sbo, p.a_layout);
         const uint64_t bdesc = make_desc(a_addr + A_BYTES, p.b_lbo, p.b_sbo, p.b_layout);
+        if (!(p.dbg & 1)) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_tf32(tmem_base, adesc + a_step * k, bdesc + b_step * k, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            const int acc = k & (p.nacc - 1);
+            umma_tf32(tmem_base + static_cast<uint32_t>(acc * p.TN), adesc + a_step * k, bdesc + b_step * k, idesc,
+                      (it > 0 || k >= p.nacc) ? 1u : 0u);
+          }
+        }
         umma_commit(empty_bar + s);
       }
       umma_commit(acc_bar);
@@ -306,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
 #pragma unroll 1
       for (int c0 = 0; c0 < TNc; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_acc(taddr + c0, TNc, p.nacc, v);
         const int ncol = min(32, Ntot - (n0 + c0));            // valid columns of this chunk
         if (row < Kw && ncol > 0) {
           float* d = dst0 + static_cast<long long>(c0) * Kw;
@@ -348,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
 #pragma unroll 1
         for (int c0 = 0; c0 < TNc; c0 += 32) {
           uint32_t v[32];
-          tmem_ld_32x32(taddr + c0, v);
+          tmem_ld_acc(taddr + c0, TNc, p.nacc, v);
           const int col = n0 + c0;
           if (valid && col < Ntot) {
             if (col + 32 <= Ntot) {
@@ -395,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
 #pragma unroll 1
         for (int c0 = 0; c0 < TNc; c0 += 32, ++chunk) {
           uint32_t vr[32];
-          tmem_ld_32x32(taddr + c0, vr);
+          tmem_ld_acc(taddr + c0, TNc, p.nacc, vr);
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = valid ? __uint_as_float(vr[j]) : 0.f;
@@ -576,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.TN));
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.TN * p.nacc));
   }
 }
 
@@ -949,6 +970,9 @@ class Program {
       (void)ctas;
       const int budget = I("smem_budget", op.side ? 56 * 1024 : 84 * 1024);
       g.stages = std::max(2, std::min(kMaxStages, budget / stage_bytes));
+      g.nacc = I("nacc", 1);     // measured: extra accumulators buy nothing (the K loop is not MMA-latency bound)
+      TORCH_CHECK((g.nacc == 1 || g.nacc == 2 || g.nacc == 4) && g.TN * g.nacc <= 512, "bad nacc");
+      g.dbg = I("dbg", 0);
       op.smem = g.stages * stage_bytes + SCRATCH_BYTES + (2 * kMaxStages + 2) * 8 + 1024;
     }
     ops_.push_back(op);

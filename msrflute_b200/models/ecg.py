@@ -73,10 +73,13 @@ class RNN(nn.Module):
         super().__init__()
         if fused and num_rnn_layers == 1:
             self.rnn_layer = FusedLSTM(input_size, hid_size)
+        elif num_rnn_layers == 1:
+            # persistent hand-written LSTM (csrc/lstm_kernels.cu); same parameter names as nn.LSTM
+            from ..ops.lstm_ops import LSTM
+            self.rnn_layer = LSTM(input_size=input_size, hidden_size=hid_size, num_layers=1, batch_first=True)
         else:
             self.rnn_layer = nn.LSTM(input_size=input_size, hidden_size=hid_size, num_layers=num_rnn_layers,
-                                     dropout=dropout_p if num_rnn_layers > 1 else 0, bidirectional=False,
-                                     batch_first=True)
+                                     dropout=dropout_p, bidirectional=False, batch_first=True)
 
     def forward(self, x):
         return self.rnn_layer(x)

@@ -4,6 +4,7 @@
 import torch
 from torch import nn
 
+from ..ops.lstm_ops import LSTM
 from .common import ClassifierModel
 
 
@@ -11,8 +12,9 @@ class CharLSTM(nn.Module):
     def __init__(self, embedding_dim=8, vocab_size=90, hidden_size=256, num_layers=2):
         super().__init__()
         self.embeddings = nn.Embedding(vocab_size, embedding_dim, padding_idx=0)
-        self.lstm = nn.LSTM(input_size=embedding_dim, hidden_size=hidden_size, num_layers=num_layers,
-                            batch_first=True)
+        # persistent hand-written LSTM (csrc/lstm_kernels.cu: W_hh resident in shared memory across the 80 steps);
+        # same parameter names / shapes / gate order as nn.LSTM, so checkpoints are interchangeable
+        self.lstm = LSTM(input_size=embedding_dim, hidden_size=hidden_size, num_layers=num_layers, batch_first=True)
         self.fc = nn.Linear(hidden_size, vocab_size)
 
     def forward(self, input_seq):
@@ -30,4 +32,4 @@ class RNN(ClassifierModel):
                             hidden_size=model_config.get("hidden_size", 256))
 
     def forward(self, x):
-        return self.net(x)      # nn.LSTM (cuDNN) manages its own precision
+        return self.net(x)

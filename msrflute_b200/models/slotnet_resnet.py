@@ -71,6 +71,9 @@ class SlotProgramBuilder:
 
     #: debugging hook: ``[lbo, sbo, kstep, layout]`` forced on every MN-major operand descriptor (tools/debug_slotnet.py)
     MN_DESC = None
+    #: measurement hooks forwarded to every GEMM launch (tools/profile_slotnet.py): accumulators per tile, debug bits
+    NACC = None
+    DBG = 0
 
     def __init__(self, W: torch.Tensor, G: torch.Tensor, batch: int, eps: float = 1e-5):
         ext = _ext.load(required=True)
@@ -138,8 +141,11 @@ class SlotProgramBuilder:
         return {"kbw": W_, "kbh": kbh, "kbb": 1, "kH": H, "kchunks": self.B * (H // kbh)}
 
     def _common(self):
-        return {"S": self.S, "B": self.B, "Warena": self.W.data_ptr(), "Garena": self.G.data_ptr(),
-                "arena_stride": self.P, "eps": self.eps}
+        d = {"S": self.S, "B": self.B, "Warena": self.W.data_ptr(), "Garena": self.G.data_ptr(),
+             "arena_stride": self.P, "eps": self.eps, "dbg": int(self.DBG)}
+        if self.NACC is not None:
+            d["nacc"] = int(self.NACC)
+        return d
 
     @staticmethod
     def _fprop_taps(cv):

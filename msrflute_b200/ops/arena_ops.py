@@ -50,20 +50,32 @@ def _2d(t: Optional[torch.Tensor]):
 
 # --------------------------------------------------------------- client step
 def fused_client_step(w, g, hyper, stats, mom=None, *, n_logical: int, nesterov: bool = False,
-                      dampening: float = 0.0, zero_grad: bool = True, first_step=None):
+                      dampening: float = 0.0, zero_grad: bool = True, first_step=None, prox_ref=None, prox_mult=None,
+                      prox_loss=None):
     """clip → sufficient stats → SGD(momentum, weight-decay) → zero grad, per arena row.
 
     ``w, g, mom``: ``[S, P]`` (or ``[P]``) fp32.  ``hyper``: ``[S, 4]`` (lr, max_norm, wd, momentum), a
     ``max_norm <= 0`` disables clipping.  ``stats``: ``[S, 4]`` accumulators (Σg, Σg², n, last ‖g‖), the
     sums are over the *clipped* gradient like the reference's.  ``first_step``: optional ``[S]`` int32 device
     flags — rows whose momentum buffer must be initialised with the gradient (torch.optim.SGD semantics).
+    ``prox_ref`` / ``prox_mult`` (``[P]`` each): FedProx — the gradient of the proximal term,
+    ``prox_mult * (w - prox_ref)``, joins ``g`` before clipping and statistics (``prox_mult`` = mu times
+    the reference's per-tensor multiplicity, 0 on padding).
     """
     w2, g2, m2 = _2d(w), _2d(g), _2d(mom)
     if _ext.use_cuda_kernels(w2, g2, hyper, stats):
         _ext.load().fused_client_step(w2, g2, hyper, stats, m2, first_step, int(n_logical), bool(nesterov),
-                                      float(dampening), bool(zero_grad))
+                                      float(dampening), bool(zero_grad), prox_ref, prox_mult, prox_loss)
         _ext.count_launch(2)
         return
+    if prox_ref is not None and prox_mult is not None:
+        diff = w2 - prox_ref.view(1, -1)
+        if prox_loss is not None:
+            prox_loss.add_(0.5 * (prox_mult.view(1, -1) * diff * diff).sum(dim=1))
+        g2 = g2 + prox_mult.view(1, -1) * diff
+        g_out = _2d(g)
+    else:
+        g_out = g2
     sumsq = (g2 * g2).sum(dim=1)
     ssum = g2.sum(dim=1)
     norm = sumsq.sqrt()
@@ -85,7 +97,69 @@ def fused_client_step(w, g, hyper, stats, mom=None, *, n_logical: int, nesterov:
         d = d + mu * new_m if nesterov else new_m
     w2.sub_(hyper[:, H_LR, None] * d)
     if zero_grad:
-        g2.zero_()
+        g_out.zero_()
+
+
+# ---------------------------------------------------------------------------------------------- slot-layout gather
+def slot_gather_bcast(W, wg_slot, wg, index_map):
+    """Model distribution into the slot arenas: ``wg_slot[j] = wg[map[j]]`` (0 on padding), ``W[s] = wg_slot`` ∀ s."""
+    if _ext.use_cuda_kernels(W, wg_slot, wg, index_map):
+        _ext.load().slot_gather_bcast(W, wg_slot, wg, index_map)
+        _ext.count_launch(1)
+        return
+    m = index_map.long()
+    row = torch.where(m >= 0, wg[m.clamp(min=0)], torch.zeros((), dtype=wg.dtype, device=wg.device))
+    wg_slot.copy_(row)
+    W.copy_(row.view(1, -1).expand_as(W))
+
+
+def slot_pg_sqnorm(W, wg_slot, out):
+    """``out[s] = ||wg_slot - W[s]||^2`` (pseudo-gradient norms for local-DP clipping / normalisation)."""
+    out.zero_()
+    if _ext.use_cuda_kernels(W, wg_slot, out):
+        _ext.load().slot_pg_sqnorm(W, wg_slot, out)
+        _ext.count_launch(1)
+        return out
+    out.copy_(((wg_slot.view(1, -1) - W) ** 2).sum(dim=1))
+    return out
+
+
+def slot_gather_fused(acc_slot, W, wg_slot, coef, sig=None, seed=None):
+    """``acc_slot += Σ_s coef[s]·(wg_slot − W[s]) + Σ_s sig[s]·N(seed[s])`` — weighting, local-DP scaling and Gaussian
+    noise of every client in one pass (all coefficients are device tensors)."""
+    if _ext.use_cuda_kernels(acc_slot, W, wg_slot, coef):
+        _ext.load().slot_gather_fused(acc_slot, W, wg_slot, coef, sig, seed)
+        _ext.count_launch(1)
+        return
+    acc_slot.add_((coef.view(-1, 1) * (wg_slot.view(1, -1) - W)).sum(dim=0))
+    if sig is not None and seed is not None:
+        for s in range(W.shape[0]):
+            if float(sig[s]) != 0.0:
+                acc_slot.add_(_philox_like_noise(acc_slot.numel(), int(seed[s]), acc_slot.device), alpha=float(sig[s]))
+
+
+def slot_scatter_acc(acc, acc_slot, index_map):
+    """``acc[map[j]] += acc_slot[j]`` then ``acc_slot = 0`` (the one pass through the permutation per round)."""
+    if _ext.use_cuda_kernels(acc, acc_slot, index_map):
+        _ext.load().slot_scatter_acc(acc, acc_slot, index_map)
+        _ext.count_launch(1)
+        return
+    m = index_map.long()
+    live = m >= 0
+    acc.index_add_(0, m[live], acc_slot[live])
+    acc_slot.zero_()
+
+
+def dead_coord_noise(acc, dead_idx, sig2_sum, seed):
+    """Local-DP noise for coordinates that no slot stores (elided dead filter taps): ``acc[idx] += sqrt(Σ sig²)·N``."""
+    if dead_idx is None or dead_idx.numel() == 0:
+        return
+    if _ext.use_cuda_kernels(acc, dead_idx, sig2_sum):
+        _ext.load().dead_coord_noise(acc, dead_idx, sig2_sum.reshape(1).float(), int(seed))
+        _ext.count_launch(1)
+        return
+    noise = _philox_like_noise(dead_idx.numel(), seed, acc.device)
+    acc.index_add_(0, dead_idx.long(), noise * float(sig2_sum.clamp(min=0).sqrt()))
 
 
 def clip_and_stats(g, hyper, stats, *, n_logical: int):

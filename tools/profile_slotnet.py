@@ -11,6 +11,42 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 
+def variants(S):
+    """Whole-step graph time under measurement hooks: accumulators per tile, MMAs off, TMA loads off."""
+    from msrflute_b200.models.resnet_gn import RESNET
+    from msrflute_b200.models.slotnet_resnet import SlotNetResNet, SlotProgramBuilder
+    from msrflute_b200.parallel.arena import ArenaLayout
+    out = []
+    for name, nacc, dbg in (("nacc=1", 1, 0), ("nacc=2", 2, 0), ("nacc=default(4)", None, 0), ("no MMA", None, 1),
+                            ("no TMA", None, 2), ("no MMA, no TMA", None, 3)):
+        SlotProgramBuilder.NACC, SlotProgramBuilder.DBG = nacc, dbg
+        torch.manual_seed(0)
+        model = RESNET({"group_norm": 2, "num_classes": 1000}).cuda()
+        layout = ArenaLayout.from_module(model)
+        plan = SlotNetResNet.plan(model, layout)
+        W = torch.randn(S, plan["numel"], device="cuda") * 0.05
+        G = torch.zeros(S, plan["numel"], device="cuda")
+        net = SlotNetResNet(model, W, G, plan, batch=20)
+        x = torch.rand(S * 20, 3, 32, 32, device="cuda") * 255
+        y = torch.randint(0, 1000, (S * 20,), device="cuda")
+        net.step(x, y)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            net.prog.run(0, -1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            g.replay()
+        e1.record()
+        e1.synchronize()
+        out.append("variant {:18s}: whole step {:.1f} us".format(name, e0.elapsed_time(e1) / 20 * 1e3))
+        del net, g
+    SlotProgramBuilder.NACC, SlotProgramBuilder.DBG = None, 0
+    return out
+
+
 def main():
     S = int(sys.argv[1]) if len(sys.argv) > 1 else 10
     from msrflute_b200.models.resnet_gn import RESNET
@@ -70,6 +106,8 @@ def main():
         e1.synchronize()
         lines.append("graph replay of the whole step, side stream {}: {:.1f} us".format(side, e0.elapsed_time(e1) / 20 * 1e3))
     lines.append("sum of isolated ops (cold L2): {:.1f} us over {} ops".format(total * 1e3, net.n_ops))
+    del net
+    lines.extend(variants(S))
     out = "\n".join(lines)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "slotnet_ops.txt"), "w") as f:
