@@ -203,12 +203,18 @@ def main():
         marks.append(e0)
     t0 = time.perf_counter()
     loss = None
+    host_marks = [t0]
     for _ in range(args.steps):
         loss = server.run_rounds(1)
+        host_marks.append(time.perf_counter())
         if cuda:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             marks.append(ev)
+    if os.environ.get("FLUTE_CKPT_TRACE") == "1":
+        slow = sorted(range(args.steps), key=lambda i: -(host_marks[i + 1] - host_marks[i]))[:4]
+        print("[bench] slowest host rounds: " + ", ".join("#{} {:.1f} ms ending t={:.3f}".format(
+            i, (host_marks[i + 1] - host_marks[i]) * 1e3, host_marks[i + 1]) for i in slow), flush=True)
     Server.sync_nodes({"phases": False})
     t1 = time.perf_counter()
     clocks = sampler.stop()

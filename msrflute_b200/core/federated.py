@@ -227,7 +227,8 @@ class Server:
             # multi-rank deferred round: the cross-rank reduction of the accumulators and of Σ weight is enqueued
             # right behind the local training; per-client records are gathered (host, gloo) only on resolve()
             yield _finish_deferred(comm, worker, local_out, len(clients), assign=assign,
-                                   cost_of=cost_of if policy == "dynamic" else None)
+                                   cost_of=cost_of if policy == "dynamic" else None,
+                                   sharded=(ctrl["extra"] or {}).get("sharded"))
             return
         for o in local_out:
             yield o
@@ -307,7 +308,7 @@ class Server:
             comm.bcast_object({"cmd": COMMAND_TERMINATE}, src=0)
 
 
-def _finish_deferred(comm, worker, local, n_clients, assign=None, cost_of=None):
+def _finish_deferred(comm, worker, local, n_clients, assign=None, cost_of=None, sharded=None):
     """Every rank calls this with its (possibly deferred / empty) local result, in the same order: NCCL/symm reduce of
     the accumulators → all-reduce of Σ weight → (on resolve) host sync + gloo gather of the per-client records."""
     from .engine import DeferredRound
@@ -319,11 +320,18 @@ def _finish_deferred(comm, worker, local, n_clients, assign=None, cost_of=None):
     # Σ weight first: with the symmetric-memory transport the server's stream is [barrier A, update kernel, barrier B]
     # and the update kernel needs the total, so the (NCCL) all-reduce must precede barrier A on every rank.
     from ..utils.timing import PHASES
-    with PHASES.phase("gather_xgpu"):
-        comm.all_reduce_(wsum)
-        comm.reduce_accumulators(acc, dst=0)
-        if comm.rank != 0 and comm.kind != "symm":
-            acc.zero_()
+    mirrors = None
+    if sharded is not None:
+        # transport v2: no all-reduce, no funnel — every rank reduces / updates / broadcasts its slice of the arena
+        with PHASES.phase("update_bcast"):
+            mirrors = comm.sharded_round(worker.weight_buffer(), acc, wsum, sharded["opt"],
+                                         noise_scale=sharded.get("noise_scale", 0.0), seed=sharded.get("seed", 0))
+    else:
+        with PHASES.phase("gather_xgpu"):
+            comm.all_reduce_(wsum)
+            comm.reduce_accumulators(acc, dst=0)
+            if comm.rank != 0 and comm.kind != "symm":
+                acc.zero_()
 
     def resolve():
         outs = local.resolve() if isinstance(local, DeferredRound) else list(local)
@@ -337,7 +345,10 @@ def _finish_deferred(comm, worker, local, n_clients, assign=None, cost_of=None):
                                                   for r, recs in enumerate(records)})
         return merged
 
-    return DeferredRound(n_clients, wsum[0], resolve)
+    dr = DeferredRound(n_clients, wsum[0], resolve)
+    dr.sharded_done = sharded is not None
+    dr.state_mirrors = mirrors
+    return dr
 
 
 def _maybe_inject_fault(rank, nround):
@@ -506,7 +517,7 @@ class Worker:
                 if ctrl.get("defer"):
                     res = self.train_clients(mine, (ctrl["lr"], None, ctrl["round"]), fused=True,
                                              extra=ctrl.get("extra"), defer=True) if mine else []
-                    _finish_deferred(comm, self, res, len(mine)).resolve()
+                    _finish_deferred(comm, self, res, len(mine), sharded=(ctrl.get("extra") or {}).get("sharded")).resolve()
                     if torch.cuda.is_available():
                         ev = torch.cuda.Event(enable_timing=True)
                         ev.record()

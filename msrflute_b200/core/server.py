@@ -288,6 +288,9 @@ class OptimizationServer(federated.Server):
         fused_weights = []
         in_sync = fused and getattr(self, "_weights_in_sync", False)
         self._weights_in_sync = False
+        sharded = self._sharded_request(fused, apply_privacy_metrics, i, num_clients_curr_iter)
+        if sharded is not None:
+            extra["sharded"] = sharded
         def consume(client_output):
             nonlocal num_clients_curr_iter
             client_stats = client_output["cs"]
@@ -332,7 +335,9 @@ class OptimizationServer(federated.Server):
             consume(client_output)
 
         fused_done = False
-        if fused and deferred is not None:
+        if fused and deferred is not None and getattr(deferred, "sharded_done", False):
+            fused_done = self._finish_sharded_round(deferred, i, num_clients_curr_iter, log_metric)
+        elif fused and deferred is not None:
             fused_done = self._fused_server_update(None, i, num_clients_curr_iter, log_metric, wsum=deferred.weight_sum)
             if not fused_done:
                 for o in deferred.resolve():
@@ -406,10 +411,7 @@ class OptimizationServer(federated.Server):
                     self.lr_weight *= self.lr_decay_factor
                     print_rank("LOG: Client weight of learning rate {}..".format(self.lr_weight))
 
-        self.backup_models(i)
-        if (i % self.model_backup_freq) == 0:
-            from ..utils.async_ckpt import flush_checkpoints
-            flush_checkpoints()         # the epoch<i>_best_* copies below read files back
+        self.backup_models(i)       # epoch<i>_* backups are queued behind pending writes (async_ckpt.submit_copy): no flush
         self.fall_back_to_prev_best_status()
         if deferred is not None:                       # everything of this round is enqueued: now read the records
             for o in deferred.resolve():
@@ -459,6 +461,34 @@ class OptimizationServer(federated.Server):
         return ((torch.cuda.is_available() or force) and not apply_privacy_metrics and not self.do_profiling
                 and not dp.get("enable_global_dp", False) and not self.config.get("dump_norm_stats", False)
                 and not self.strategy.skip_model_update)
+
+    def _sharded_request(self, fused, apply_privacy_metrics, curr_iter, num_clients_curr_iter):
+        """Transport v2 is used for a round when every rank can run its slice of the server step: symmetric-memory
+        transport, deferred fused round, element-wise server optimizer, nothing that needs the aggregate on one GPU
+        (norm logging / clipping, server replay, fall-back-to-best)."""
+        comm = federated.get_comm()
+        if not fused or comm.size == 1 or getattr(comm, "kind", "") != "symm" or not self._can_defer(apply_privacy_metrics):
+            return None
+        if not getattr(comm, "supports_sharded", lambda: False)():
+            return None
+        if self.server_trainer is not None or self.fall_back_to_best_model or self.config.get("dump_norm_stats", False):
+            return None
+        opt = self.worker_trainer.sharded_step_params()
+        if opt is None:
+            return None
+        return {"opt": opt, "noise_scale": 0.0, "seed": 0}
+
+    def _finish_sharded_round(self, deferred, curr_iter, num_clients_curr_iter, log_metric):
+        worker = self.single_worker or federated._Runtime.worker
+        self.worker_trainer.finish_sharded_step(worker.weight_buffer(), getattr(deferred, "state_mirrors", None))
+        self._weights_in_sync = True
+        self.strategy.client_weights, self.strategy.client_parameters_stack = [], []
+        if type(self.strategy).__name__ == "DGA":
+            from ..extensions import privacy
+            privacy.update_privacy_accountant(self.config, len(self.client_idx_list), curr_iter=curr_iter,
+                                              num_clients_curr_iter=num_clients_curr_iter, metric_logger=log_metric)
+        self.losses = self.worker_trainer.run_lr_scheduler(force_run_val=False)
+        return True
 
     def _fused_server_update(self, weights, curr_iter, num_clients_curr_iter, log_metric, wsum=None):
         """Fast path: the weighted pseudo-gradient sums (already reduced onto this rank, or peer-mapped when the
@@ -529,10 +559,15 @@ class OptimizationServer(federated.Server):
         if (i % self.model_backup_freq) == 0:
             self.worker_trainer.save(model_path=self.model_path, token="epoch{}".format(i),
                                      config=self.config["server_config"])
+            from . import trainer as _trainer_mod
             for body in ("best_val_acc", "best_val_loss", "best_test_acc"):
                 src = os.path.join(self.model_path, "{}_model.tar".format(body))
-                if os.path.exists(src):
-                    shutil.copyfile(src, os.path.join(self.model_path, "epoch{}_{}_model.tar".format(i, body)))
+                dst = os.path.join(self.model_path, "epoch{}_{}_model.tar".format(i, body))
+                if _trainer_mod.ASYNC_CHECKPOINTS["enabled"]:
+                    from ..utils.async_ckpt import get_checkpointer
+                    get_checkpointer().submit_copy(src, dst)          # off the training thread, after pending writes
+                elif os.path.exists(src):
+                    shutil.copyfile(src, dst)
 
     def fall_back_to_prev_best_status(self):
         if not self.fall_back_to_best_model:

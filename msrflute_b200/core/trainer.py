@@ -184,6 +184,41 @@ class ModelUpdater(TrainerBase):
         if step is not None:
             st.step = step
 
+    def sharded_step_params(self):
+        """Hyper-parameters of the NEXT server step for the sharded (every-rank) update kernel, or ``None`` when this
+        optimizer / configuration needs the single-GPU path (layer-wise trust ratios, server-side clipping)."""
+        fs = self.fused_state()
+        if fs is None or self.max_grad_norm:
+            return None
+        st = fs[0]
+        if st.kind in ("lamb", "LarsSGD"):
+            return None
+        if (st.m is not None or st.v is not None) and st.step > 0 and not getattr(self, "_sharded_started", False):
+            return None                  # resumed optimizer state lives on the server only: keep the single-GPU path
+        self._sharded_started = True
+        g = self.optimizer.param_groups[0]
+        return {"code": st.code, "step": st.step + 1, "lr": float(g["lr"]), "betas": tuple(st.betas), "eps": st.eps,
+                "weight_decay": st.weight_decay, "momentum": st.momentum, "dampening": st.dampening,
+                "nesterov": st.nesterov, "correct_bias": st.correct_bias, "need_m": st.m is not None,
+                "need_v": st.v is not None}
+
+    def finish_sharded_step(self, w_buf, state_mirrors):
+        """Server side of a sharded round: the new weights are in the (symmetric) weight buffer, the optimizer state of
+        every slice was mirrored into ``state_mirrors`` — refresh the model arena and the checkpointable state."""
+        st = self.fused_state()[0]
+        module_arena(self.model)[0].flat.copy_(w_buf)
+        if state_mirrors is not None:
+            if st.m is not None and state_mirrors[0] is not None:
+                st.m.copy_(state_mirrors[0])
+            if st.v is not None and state_mirrors[1] is not None:
+                st.v.copy_(state_mirrors[1])
+        st.step += 1
+        self.optimizer._opt_called = True
+        for p in self.model.parameters():
+            s = self.optimizer.state.get(p)
+            if s is not None and "step" in s:
+                s["step"] = st.step if not torch.is_tensor(s["step"]) else torch.tensor(float(st.step))
+
     def fused_update(self, accs, weight_sum, noise_scale=0.0, seed=0, bcast=None, stats_out=None, grad_out=None):
         """One fused pass: Σ_ranks acc / Σw (+noise) (+clip) → optimizer → broadcast.  Returns False when the
         configuration has no fused kernel (caller falls back to ``update_model``)."""

@@ -24,6 +24,12 @@ void server_update(torch::Tensor w, std::vector<torch::Tensor> accs, torch::Tens
                    double eps, double wd, double mom, double damp, bool nesterov, bool correct_bias, double noise_scale,
                    int64_t seed, double max_grad_norm, bool zero_accs);
 void p2p_broadcast(torch::Tensor src, std::vector<torch::Tensor> dsts);
+void sharded_server_update(std::vector<torch::Tensor> ws, std::vector<torch::Tensor> accs, std::vector<torch::Tensor> wsums,
+                           c10::optional<torch::Tensor> m, c10::optional<torch::Tensor> v,
+                           std::vector<torch::Tensor> m_mirror, std::vector<torch::Tensor> v_mirror, int64_t acc_mc,
+                           int64_t w_mc, int64_t rank, int64_t kind, int64_t step, double lr, double b1, double b2,
+                           double eps, double wd, double mom, double damp, bool nesterov, bool correct_bias,
+                           double noise_scale, int64_t seed);
 std::vector<torch::Tensor> group_norm_fwd(torch::Tensor x, torch::Tensor weight, torch::Tensor bias,
                                           c10::optional<torch::Tensor> residual, int64_t G, double eps, bool relu,
                                           bool per_group_affine, int64_t sets);
@@ -95,6 +101,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("accumulate_pseudo_grad", &flute::accumulate_pseudo_grad);
   m.def("server_update", &flute::server_update);
   m.def("p2p_broadcast", &flute::p2p_broadcast);
+  m.def("sharded_server_update", &flute::sharded_server_update);
   m.def("group_norm_fwd", &flute::group_norm_fwd);
   m.def("group_norm_bwd", &flute::group_norm_bwd);
 

@@ -306,6 +306,110 @@ void server_update(torch::Tensor w, std::vector<torch::Tensor> accs, torch::Tens
   FLUTE_CUDA_CHECK(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------------ sharded update
+// Transport v2: EVERY rank runs this kernel on its own 1/N slice of the arena —
+//     g[i]   = sum_r acc_r[i] / sum_r wsum_r        P2P loads from every rank's accumulator slice, or ONE
+//                                                   multimem.ld_reduce through the NVSwitch multicast object (NVLS)
+//     w[i]   = OPT(w[i], g[i], state[i])            optimizer state exists only for the rank's slice (ZeRO-1)
+//     w_r[i] = w[i] for every rank r                P2P stores, or ONE multimem.st
+// so a GPU moves (N-1)/N * P floats each way instead of (N-1) * P through the server's links, sum(weights) travels as a
+// symmetric scalar (no NCCL all-reduce), and the Philox counter is the GLOBAL quad index (noise is shard-invariant).
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc_ptr) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc_ptr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st(float* mc_ptr, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               :: "l"(mc_ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(kT)
+sharded_update_kernel(float* __restrict__ w_local, PtrList accs, PtrList wsums, float* __restrict__ m, float* __restrict__ v,
+                      PtrList bcast, PtrList m_mirror, PtrList v_mirror, const float* acc_mc, float* w_mc, int64_t q_lo,
+                      int64_t q_hi, OptParams o, float noise_scale, uint64_t seed) {
+  float tot = 0.f;
+  for (int r = 0; r < wsums.n; ++r) {
+    float t;
+    asm volatile("ld.global.relaxed.sys.f32 %0, [%1];" : "=f"(t) : "l"(wsums.p[r]) : "memory");
+    tot += t;
+  }
+  const float inv = 1.f / tot;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kT;
+  for (int64_t i = q_lo + static_cast<int64_t>(blockIdx.x) * kT + threadIdx.x; i < q_hi; i += stride) {
+    float4 g = acc_mc != nullptr ? multimem_ld_reduce_add(acc_mc + 4 * i) : gather_sum(accs, i);
+    g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
+    if (noise_scale > 0.f) {
+      const float4 z = philox_normal4(seed, static_cast<uint64_t>(i));
+      g.x = fmaf(noise_scale, z.x, g.x); g.y = fmaf(noise_scale, z.y, g.y);
+      g.z = fmaf(noise_scale, z.z, g.z); g.w = fmaf(noise_scale, z.w, g.w);
+    }
+    float4 ww = ld_na(reinterpret_cast<const float4*>(w_local) + i);
+    float4 mm = m ? ld_na(reinterpret_cast<const float4*>(m) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 vv = v ? ld_na(reinterpret_cast<const float4*>(v) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ww.x = opt_elem(o, ww.x, g.x, mm.x, vv.x); ww.y = opt_elem(o, ww.y, g.y, mm.y, vv.y);
+    ww.z = opt_elem(o, ww.z, g.z, mm.z, vv.z); ww.w = opt_elem(o, ww.w, g.w, mm.w, vv.w);
+    if (m) st_stream(reinterpret_cast<float4*>(m) + i, mm);
+    if (v) st_stream(reinterpret_cast<float4*>(v) + i, vv);
+    for (int r = 0; r < m_mirror.n; ++r) st_stream(reinterpret_cast<float4*>(m_mirror.p[r]) + i, mm);   // checkpoint copy on the server
+    for (int r = 0; r < v_mirror.n; ++r) st_stream(reinterpret_cast<float4*>(v_mirror.p[r]) + i, vv);
+    if (w_mc != nullptr) {
+      multimem_st(w_mc + 4 * i, ww);
+    } else {
+      for (int r = 0; r < bcast.n; ++r) st_stream(reinterpret_cast<float4*>(bcast.p[r]) + i, ww);
+    }
+  }
+}
+
+static PtrList to_list_any(const std::vector<torch::Tensor>& ts) {
+  PtrList l;
+  l.n = 0;
+  TORCH_CHECK(ts.size() <= static_cast<size_t>(kMaxPeers), "too many peers");
+  for (const auto& t : ts) {
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kFloat32, "fp32 CUDA peer buffer expected");
+    l.p[l.n++] = t.data_ptr<float>();
+  }
+  return l;
+}
+
+// ws / accs / wsums: every rank's weight buffer / accumulator / sum(weights) scalar (peer mapped; index == rank).
+// m, v: this rank's optimizer state (full-size buffers, only the slice is touched); m_mirror / v_mirror: buffers that
+// additionally receive the slice (the server's state arenas, for checkpoints).  acc_mc / w_mc: multicast addresses of
+// the accumulator / weight buffers (0 = P2P loops).  Returns nothing; the caller brackets it with device barriers.
+void sharded_server_update(std::vector<torch::Tensor> ws, std::vector<torch::Tensor> accs, std::vector<torch::Tensor> wsums,
+                           c10::optional<torch::Tensor> m, c10::optional<torch::Tensor> v,
+                           std::vector<torch::Tensor> m_mirror, std::vector<torch::Tensor> v_mirror, int64_t acc_mc,
+                           int64_t w_mc, int64_t rank, int64_t kind, int64_t step, double lr, double b1, double b2,
+                           double eps, double wd, double mom, double damp, bool nesterov, bool correct_bias,
+                           double noise_scale, int64_t seed) {
+  const int N = static_cast<int>(ws.size());
+  TORCH_CHECK(N >= 1 && static_cast<int>(accs.size()) == N && static_cast<int>(wsums.size()) == N && rank >= 0 && rank < N);
+  TORCH_CHECK(kind != LAMB && kind != LARS, "layer-wise optimizers are not sharded");
+  const int64_t P = ws[rank].numel();
+  TORCH_CHECK(P % 4 == 0);
+  const c10::cuda::CUDAGuard guard(ws[rank].device());
+  const int64_t n4 = P >> 2;
+  int64_t per = (n4 + N - 1) / N;
+  per = (per + 31) / 32 * 32;                                   // slices start on 512-byte boundaries
+  const int64_t lo = std::min<int64_t>(n4, rank * per), hi = std::min<int64_t>(n4, lo + per);
+  if (hi <= lo) return;
+  OptParams o;
+  o.kind = static_cast<int>(kind); o.step = static_cast<int>(step);
+  o.lr = static_cast<float>(lr); o.b1 = static_cast<float>(b1); o.b2 = static_cast<float>(b2);
+  o.eps = static_cast<float>(eps); o.wd = static_cast<float>(wd); o.mom = static_cast<float>(mom);
+  o.damp = static_cast<float>(damp); o.nesterov = nesterov; o.correct_bias = correct_bias;
+  o.bc1 = static_cast<float>(1.0 - std::pow(b1, static_cast<double>(step)));
+  o.bc2 = static_cast<float>(1.0 - std::pow(b2, static_cast<double>(step)));
+  PtrList A = to_list(accs, P), B = to_list(ws, P), WS = to_list_any(wsums);
+  PtrList MM = to_list_any(m_mirror), VM = to_list_any(v_mirror);
+  sharded_update_kernel<<<grid_for(hi - lo), kT, 0, at::cuda::getCurrentCUDAStream()>>>(
+      ws[rank].data_ptr<float>(), A, WS, m.has_value() ? m->data_ptr<float>() : nullptr,
+      v.has_value() ? v->data_ptr<float>() : nullptr, B, MM, VM, reinterpret_cast<const float*>(acc_mc),
+      reinterpret_cast<float*>(w_mc), lo, hi, o, static_cast<float>(noise_scale), static_cast<uint64_t>(seed));
+  FLUTE_CUDA_CHECK(cudaGetLastError());
+}
+
 // Plain P2P copy kernel: dst_r[i] = src[i] for every peer (explicit broadcast at round 0 / after checkpoint loads).
 __global__ void __launch_bounds__(kT) bcast_copy_kernel(const float* __restrict__ src, PtrList dst, int64_t P) {
   const int64_t n4 = P >> 2, stride = static_cast<int64_t>(gridDim.x) * kT;

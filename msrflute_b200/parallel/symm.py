@@ -116,6 +116,65 @@ class SymmComm(CollectiveComm):
         name, _ = self._handle_of(w)
         return self._peers(name) if name is not None else None
 
+    # ---- transport v2: every rank reduces + updates + broadcasts 1/N of the arena -------------------------
+    def supports_sharded(self):
+        import os
+        return os.environ.get("FLUTE_SHARDED_UPDATE", "1") != "0" and hasattr(self._ext, "sharded_server_update")
+
+    def sharded_round(self, w_buf, acc, local_wsum, opt, noise_scale=0.0, seed=0):
+        """Called by EVERY rank, once per round, with the same ``opt`` (the server optimizer's hyper-parameters of this
+        step): [sum(weights) -> symmetric scalar] [barrier A] [sharded kernel: P2P / NVLS reduce of my slice of every
+        accumulator -> optimizer -> store of my slice into every rank's weight buffer] [barrier B] [zero my accumulator].
+        No NCCL call and no single-GPU funnel on the path.  Returns the rank-0 mirrors of the optimizer state
+        (``(m, v)`` symmetric buffers, or ``None``) so the server can refresh its checkpointable state."""
+        import os
+        name_w, hdl_w = self._handle_of(w_buf)
+        name_a, hdl_a = self._handle_of(acc)
+        assert name_w is not None and name_a is not None, "sharded update needs symmetric weight / accumulator buffers"
+        P = w_buf.numel()
+        if "wsum" not in self._bufs:                         # collective allocation: every rank is in the same round
+            self._alloc("wsum", 32, torch.float32)
+        wsum_t = self._bufs["wsum"][0]
+        wsum_t[0:1].copy_(local_wsum.reshape(1).to(wsum_t.dtype))
+        kind = int(opt["code"])
+        need_m = bool(opt.get("need_m", False))
+        need_v = bool(opt.get("need_v", False))
+        m = v = None
+        m_mirror, v_mirror = [], []
+        if need_m:
+            if "m_srv" not in self._bufs:
+                self._alloc("m_srv", P, torch.float32)
+            if getattr(self, "_m_shard", None) is None:
+                self._m_shard = torch.zeros(P, device=w_buf.device)
+            m = self._m_shard
+            m_mirror = [self._peers("m_srv")[0]]
+        if need_v:
+            if "v_srv" not in self._bufs:
+                self._alloc("v_srv", P, torch.float32)
+            if getattr(self, "_v_shard", None) is None:
+                self._v_shard = torch.zeros(P, device=w_buf.device)
+            v = self._v_shard
+            v_mirror = [self._peers("v_srv")[0]]
+        use_nvls = os.environ.get("FLUTE_NVLS", "1") != "0"
+        acc_mc = int(getattr(hdl_a, "multicast_ptr", 0) or 0) if use_nvls else 0
+        w_mc = int(getattr(hdl_w, "multicast_ptr", 0) or 0) if use_nvls else 0
+        if not (acc_mc and w_mc):
+            acc_mc = w_mc = 0
+        self.last_sharded_mode = "nvls-multimem" if acc_mc else "p2p"
+        hdl_a.barrier()                                      # A: every accumulator and sum(weights) is final
+        b1, b2 = opt.get("betas", (0.9, 0.999))
+        self._ext.sharded_server_update(
+            self._peers(name_w), self._peers(name_a), self._peers("wsum"), m, v, m_mirror, v_mirror, acc_mc, w_mc,
+            self.rank, kind, int(opt["step"]), float(opt["lr"]), float(b1), float(b2), float(opt.get("eps", 1e-8)),
+            float(opt.get("weight_decay", 0.0)), float(opt.get("momentum", 0.0)), float(opt.get("dampening", 0.0)),
+            bool(opt.get("nesterov", False)), bool(opt.get("correct_bias", True)), float(noise_scale), int(seed))
+        _ext.count_launch(1)
+        hdl_a.barrier()                                      # B: every slice is everywhere
+        acc.zero_()
+        if self.rank == 0 and (need_m or need_v):
+            return (self._bufs["m_srv"][0] if need_m else None, self._bufs["v_srv"][0] if need_v else None)
+        return None
+
     def round_done(self, acc):
         """Barrier B on the server (after its update kernel consumed every accumulator and wrote every weight copy)."""
         name, hdl = self._handle_of(acc)

@@ -107,8 +107,8 @@ class AsyncCheckpointer:
     the GIL (every torch call re-acquires it).  Snapshots are still taken every round (latest wins); the file on disk
     is at most ``min_interval`` (+ one write) stale, and ``flush()`` always writes the newest snapshot."""
 
-    def __init__(self, min_interval: float = 0.25):
-        self.min_interval = float(min_interval)
+    def __init__(self, min_interval: float = 0.5):
+        self.min_interval = float(os.environ.get("FLUTE_CKPT_MIN_INTERVAL", min_interval))
         import sys
         sys.setswitchinterval(min(sys.getswitchinterval(), 0.0005))   # bound GIL hand-over latency to the trainer
         self._last_write = {}              # path -> time of the last completed write
@@ -140,6 +140,14 @@ class AsyncCheckpointer:
             if path in self._pending:
                 self.coalesced += 1
             self._pending[path] = (snap, ev)
+            self._wake.notify()
+
+    def submit_copy(self, src: str, dst: str):
+        """Copy ``src`` to ``dst`` off the training thread (the periodic ``epoch<i>_best_*`` backups: three 47 MB file
+        copies every ``model_backup_freq`` rounds would otherwise stall that round by ~70 ms).  A pending write of
+        ``src`` is flushed first, so the copy is of the newest snapshot."""
+        with self._wake:
+            self._pending[dst] = (("copy", src), None)
             self._wake.notify()
 
     def submit_text(self, path: str, text: str):
@@ -175,13 +183,41 @@ class AsyncCheckpointer:
                 self._busy += 1
             try:
                 tmp = path + ".tmp"
-                if isinstance(snap, str):
+                if isinstance(snap, tuple) and snap and snap[0] == "copy":
+                    src = snap[1]
+                    with self._wake:
+                        queued = self._pending.pop(src, None)
+                    if queued is not None:                 # newest snapshot of the source first
+                        q_snap, q_ev = queued
+                        if isinstance(q_snap, str):
+                            with open(src + ".tmp", "w", encoding="utf8") as f:
+                                f.write(q_snap)
+                        else:
+                            if q_ev is not None:
+                                q_ev.synchronize()
+                            torch.save(_to_host(q_snap), src + ".tmp")
+                        os.replace(src + ".tmp", src)
+                    if os.path.exists(src):
+                        import shutil
+                        shutil.copyfile(src, tmp)
+                    else:
+                        continue
+                elif isinstance(snap, str):
                     with open(tmp, "w", encoding="utf8") as f:
                         f.write(snap)
                 else:
+                    import time as _t
+                    t0 = _t.perf_counter()
                     if ev is not None:
                         ev.synchronize()
-                    torch.save(_to_host(snap), tmp)
+                    t1 = _t.perf_counter()
+                    host = _to_host(snap)
+                    t2 = _t.perf_counter()
+                    torch.save(host, tmp)
+                    t3 = _t.perf_counter()
+                    if os.environ.get("FLUTE_CKPT_TRACE") == "1":
+                        print("[ckpt] {} wait {:.1f} ms, d2h {:.1f} ms, torch.save {:.1f} ms at t={:.3f}".format(
+                            os.path.basename(path), (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, t3), flush=True)
                 os.replace(tmp, path)
                 self._last_write[path] = time.monotonic()
                 self.written += 1
