@@ -76,6 +76,14 @@ at::Tensor cosine_stats(at::Tensor a, at::Tensor b);
 std::vector<at::Tensor> max_pool2d_fwd(at::Tensor x, int64_t k, int64_t stride, int64_t pad);
 at::Tensor max_pool2d_bwd(at::Tensor dy, at::Tensor arg, int64_t H, int64_t W, int64_t k, int64_t stride, int64_t pad);
 void bind_slotnet(pybind11::module_& m);
+torch::Tensor embedding_fwd(torch::Tensor idx, torch::Tensor weight);
+torch::Tensor embedding_bwd(torch::Tensor idx, torch::Tensor dy, int64_t V, int64_t padding_idx);
+torch::Tensor dropout_apply(torch::Tensor x, double p, torch::Tensor seed, bool backward);
+std::vector<torch::Tensor> batch_norm_fwd(torch::Tensor x, c10::optional<torch::Tensor> gamma, c10::optional<torch::Tensor> beta,
+                                          c10::optional<torch::Tensor> residual, c10::optional<torch::Tensor> run_mean,
+                                          c10::optional<torch::Tensor> run_var, double momentum, double eps, bool relu);
+std::vector<torch::Tensor> batch_norm_bwd(torch::Tensor dy, torch::Tensor x, torch::Tensor y, c10::optional<torch::Tensor> gamma,
+                                          torch::Tensor stats, bool relu, bool want_dres);
 bool lstm_supported(int64_t H);
 std::vector<torch::Tensor> lstm_layer_fwd(torch::Tensor gx, torch::Tensor whh, c10::optional<torch::Tensor> h0,
                                           c10::optional<torch::Tensor> c0);
@@ -131,6 +139,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lstm_cell_fwd", &flute::lstm_cell_fwd);
   m.def("lstm_cell_bwd", &flute::lstm_cell_bwd);
   flute::bind_slotnet(m);
+  m.def("embedding_fwd", &flute::embedding_fwd);
+  m.def("embedding_bwd", &flute::embedding_bwd);
+  m.def("dropout_apply", &flute::dropout_apply);
+  m.def("batch_norm_fwd", &flute::batch_norm_fwd);
+  m.def("batch_norm_bwd", &flute::batch_norm_bwd);
   m.def("lstm_supported", &flute::lstm_supported);
   m.def("lstm_layer_fwd", &flute::lstm_layer_fwd);
   m.def("lstm_layer_bwd", &flute::lstm_layer_bwd);

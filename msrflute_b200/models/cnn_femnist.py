@@ -4,6 +4,7 @@ FC 128→{10|62}.  1,206,590 parameters with 62 classes."""
 import torch
 from torch import nn
 
+from ..ops.nn_ops import Dropout
 from .common import ClassifierModel
 
 
@@ -13,9 +14,9 @@ class CNN_DropOut(nn.Module):
         self.conv2d_1 = nn.Conv2d(1, 32, kernel_size=3)
         self.conv2d_2 = nn.Conv2d(32, 64, kernel_size=3)
         self.max_pooling = nn.MaxPool2d(2, stride=2)
-        self.dropout_1 = nn.Dropout(0.25)
+        self.dropout_1 = Dropout(0.25)          # Philox mask recomputed in the backward (csrc/nn_kernels.cu)
         self.linear_1 = nn.Linear(9216, 128)
-        self.dropout_2 = nn.Dropout(0.5)
+        self.dropout_2 = Dropout(0.5)
         self.linear_2 = nn.Linear(128, 10 if only_digits else 62)
 
     def forward(self, x):

@@ -48,7 +48,18 @@ class GroupNorm2d(nn.Module):
 
 
 class _BN(nn.BatchNorm2d):
+    """BatchNorm2d — what the reference's RESNET instantiates as shipped (model.py:116).  Training-mode forward /
+    backward with the residual add and ReLU fused run on ``csrc/nn_kernels.cu`` (one CTA per channel); evaluation
+    (running statistics) is a plain affine map."""
+
     def forward(self, x, residual=None, relu=False):
+        if self.training and x.is_cuda and x.dtype == torch.float32 and self.affine and self.track_running_stats:
+            from ..ops import nn_ops
+            if self.momentum is not None:
+                if self.num_batches_tracked is not None:
+                    self.num_batches_tracked.add_(1)
+                return nn_ops.batch_norm_train(x, self.weight, self.bias, self.running_mean, self.running_var,
+                                               self.momentum, self.eps, residual=residual, relu=relu)
         y = super().forward(x)
         if residual is not None:
             y = y + residual

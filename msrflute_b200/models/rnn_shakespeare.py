@@ -5,13 +5,14 @@ import torch
 from torch import nn
 
 from ..ops.lstm_ops import LSTM
+from ..ops.nn_ops import Embedding
 from .common import ClassifierModel
 
 
 class CharLSTM(nn.Module):
     def __init__(self, embedding_dim=8, vocab_size=90, hidden_size=256, num_layers=2):
         super().__init__()
-        self.embeddings = nn.Embedding(vocab_size, embedding_dim, padding_idx=0)
+        self.embeddings = Embedding(vocab_size, embedding_dim, padding_idx=0)      # csrc/nn_kernels.cu gather / scatter-add
         # persistent hand-written LSTM (csrc/lstm_kernels.cu: W_hh resident in shared memory across the 80 steps);
         # same parameter names / shapes / gate order as nn.LSTM, so checkpoints are interchangeable
         self.lstm = LSTM(input_size=embedding_dim, hidden_size=hidden_size, num_layers=num_layers, batch_first=True)
