@@ -128,9 +128,12 @@ class DeviceClientEngine:
             return False
         dp = cfg.get("dp_config", None) or {}
         # local DP (DGA): clip / normalise + Gaussian noise are fused into the gather; FedProx: closed-form proximal
-        # gradient in the fused step.  Gradient quantization still takes the generic per-client path.
+        # gradient in the fused step; gradient quantization (DGA): radix-select statistics + binning fused into the gather.
         if cc.get("quant_thresh", None) is not None:
-            return False
+            if strategy != "dga":
+                return False                   # only DGA quantizes in the reference (dga.py:149)
+            if dp.get("enable_local_dp", False) and float(dp.get("eps", -1)) >= 0:
+                return False                   # quantizing a noised gradient needs it materialised: generic path
         if dp.get("enable_local_dp", False) and strategy != "dga":
             return False
         pm = cfg.get("privacy_metrics_config", None) or {}
@@ -423,6 +426,32 @@ class DeviceClientEngine:
             return None
         return self.wg_slot if self.wg_slot is not None else self._w_ref
 
+    def _quant_tables(self):
+        """(segs [T, 3], seg_of_blk [P / 32]) of the slot layout for the fused quantization kernels."""
+        if getattr(self, "_qtab", None) is None:
+            lay = self.layout
+            P = int(self.W.shape[1])
+            names = lay.names
+            if self.slot_plan is not None:
+                offs = [int(self.slot_plan["offsets"][n]) for n in names]
+                order = sorted(range(len(offs)), key=lambda i: offs[i])
+                ends = {order[k]: (offs[order[k + 1]] if k + 1 < len(order) else P) for k in range(len(order))}
+                m = self.index_map.cpu()
+                # iterated span = up to the tensor's last stored element (internal layout padding is iterated as zeros;
+                # the kernels correct the zero count with total - span, which may be negative)
+                live = []
+                for i in range(len(offs)):
+                    pos = (m[offs[i]:ends[i]] >= 0).nonzero()
+                    live.append(int(pos.max()) + 1 if pos.numel() else 0)
+            else:
+                offs, live = list(lay.offsets), list(lay.sizes)
+            segs = torch.tensor([[o, n, int(nt)] for o, n, nt in zip(offs, live, lay.sizes)], dtype=torch.int64)
+            blk = torch.full((P // 32,), -1, dtype=torch.int16)
+            for t, (o, n) in enumerate(zip(offs, live)):
+                blk[o // 32:(o + n + 31) // 32] = t
+            self._qtab = (segs.to(self.device), blk.to(self.device))
+        return self._qtab
+
     def _dead_coords(self):
         """Global-arena positions of real parameters that no slot stores (elided dead filter taps)."""
         if self._dead_idx is None:
@@ -614,7 +643,15 @@ class DeviceClientEngine:
                 else:
                     self.weights.copy_(w * actf)
                     coef = self.weights
-                arena_ops.slot_gather_fused(acc_row, self.W, wg_row, coef, sig, seeds)
+                q_thresh = cfg["client_config"].get("quant_thresh", None)
+                if q_thresh is not None and strategy == "dga":
+                    # gradient quantization of every client's payload (ref. quant.py), statistics by radix select
+                    bits = int(cfg["client_config"].get("quant_bits", 8))
+                    segs, seg_of_blk = self._quant_tables()
+                    qparams = arena_ops.slot_quant_stats(self.W, wg_row, segs, float(q_thresh), bits)
+                    arena_ops.slot_quant_gather(acc_row, self.W, wg_row, coef, qparams, seg_of_blk, bits)
+                else:
+                    arena_ops.slot_gather_fused(acc_row, self.W, wg_row, coef, sig, seeds)
                 if self.index_map is not None:
                     arena_ops.slot_scatter_acc(acc, self.acc_slot, self.index_map)
                     if sig is not None:

@@ -76,6 +76,9 @@ at::Tensor cosine_stats(at::Tensor a, at::Tensor b);
 std::vector<at::Tensor> max_pool2d_fwd(at::Tensor x, int64_t k, int64_t stride, int64_t pad);
 at::Tensor max_pool2d_bwd(at::Tensor dy, at::Tensor arg, int64_t H, int64_t W, int64_t k, int64_t stride, int64_t pad);
 void bind_slotnet(pybind11::module_& m);
+torch::Tensor slot_quant_stats(torch::Tensor W, torch::Tensor wg, torch::Tensor segs, double q, int64_t bits);
+void slot_quant_gather(torch::Tensor acc_slot, torch::Tensor W, torch::Tensor wg, torch::Tensor coef, torch::Tensor params,
+                       torch::Tensor seg_of_blk, int64_t bits);
 torch::Tensor embedding_fwd(torch::Tensor idx, torch::Tensor weight);
 torch::Tensor embedding_bwd(torch::Tensor idx, torch::Tensor dy, int64_t V, int64_t padding_idx);
 torch::Tensor dropout_apply(torch::Tensor x, double p, torch::Tensor seed, bool backward);
@@ -139,6 +142,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lstm_cell_fwd", &flute::lstm_cell_fwd);
   m.def("lstm_cell_bwd", &flute::lstm_cell_bwd);
   flute::bind_slotnet(m);
+  m.def("slot_quant_stats", &flute::slot_quant_stats);
+  m.def("slot_quant_gather", &flute::slot_quant_gather);
   m.def("embedding_fwd", &flute::embedding_fwd);
   m.def("embedding_bwd", &flute::embedding_bwd);
   m.def("dropout_apply", &flute::dropout_apply);

@@ -162,6 +162,59 @@ def dead_coord_noise(acc, dead_idx, sig2_sum, seed):
     acc.index_add_(0, dead_idx.long(), noise * float(sig2_sum.clamp(min=0).sqrt()))
 
 
+def slot_quant_stats(W, wg_row, segs, q: float, bits: int):
+    """Per (slot, tensor) quantization statistics of the pseudo-gradient ``wg_row − W[s]``: ``[S, T, 4]`` =
+    (min, bin width, |g|-quantile threshold, max).  ``segs``: int64 ``[T, 3]`` (offset, stored elements, elements of the
+    full tensor — the difference are structurally-zero entries the slot layout does not store).  CUDA: radix select
+    (``csrc/quant_gather.cu``); the PyTorch path below (``torch.quantile`` on the full tensor) is the oracle."""
+    if _ext.use_cuda_kernels(W, wg_row, segs):
+        out = _ext.load().slot_quant_stats(W, wg_row, segs, float(q), int(bits))
+        _ext.count_launch(9)
+        return out
+    S, T = W.shape[0], segs.shape[0]
+    out = torch.zeros(S, T, 4, dtype=torch.float32, device=W.device)
+    for s in range(S):
+        for t, (off, n, ntot) in enumerate(segs.tolist()):
+            d = (wg_row[off:off + n] - W[s, off:off + n]).float()
+            full = torch.cat([d, d.new_zeros(ntot - n)]) if ntot > n else d
+            lo, hi = full.min(), full.max()
+            a = full.abs()
+            if a.numel() > 2 ** 24:
+                pos = q * (a.numel() - 1)
+                srt = a.sort().values
+                k0 = int(pos)
+                thr = srt[k0] + (pos - k0) * (srt[min(k0 + 1, a.numel() - 1)] - srt[k0])
+            else:
+                thr = torch.quantile(a, q)
+            out[s, t] = torch.stack([lo, (hi - lo) / (2 ** bits - 1), thr, hi])
+    return out
+
+
+def slot_quant_gather(acc_row, W, wg_row, coef, params, seg_of_blk, bits: int):
+    """``acc_row[j] += Σ_s coef[s]·Q_{s,t(j)}(wg_row[j] − W[s, j])`` — binning to ``2**bits`` levels on ``[lo, hi]``,
+    zeroing below the threshold and the aggregation weight in one pass (ref. ``extensions/quantization/quant.py:53-100``
+    applied to every client's payload)."""
+    if _ext.use_cuda_kernels(acc_row, W, wg_row, coef, params, seg_of_blk):
+        _ext.load().slot_quant_gather(acc_row, W, wg_row, coef, params, seg_of_blk, int(bits))
+        _ext.count_launch(1)
+        return
+    L = 2 ** bits
+    seg = seg_of_blk.long().repeat_interleave(32)
+    live = seg >= 0
+    segc = seg.clamp(min=0)
+    for s in range(W.shape[0]):
+        c = float(coef[s])
+        if c == 0.0:
+            continue
+        d = wg_row - W[s]
+        lo, width, thr = params[s, segc, 0], params[s, segc, 1], params[s, segc, 2]
+        safe = torch.where(width > 0, width, torch.ones_like(width))
+        idx = torch.ceil((d - lo) / safe - 0.5).clamp(0, L - 1)
+        binned = torch.where(width > 0, lo + idx * width, lo)
+        qd = torch.where((d.abs() > thr) & live, binned, torch.zeros_like(d))
+        acc_row.add_(qd, alpha=c)
+
+
 def clip_and_stats(g, hyper, stats, *, n_logical: int):
     """Clip in place + accumulate stats, for client optimizers other than SGD (the step is then done by torch)."""
     g2 = _2d(g)

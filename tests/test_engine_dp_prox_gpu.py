@@ -167,3 +167,77 @@ def test_engine_fedprox_and_noisy_dp_rounds_run(task):
     losses = [server.run_rounds(1) for _ in range(3)]
     server.end_training()
     assert all(math.isfinite(v) for v in losses), losses
+
+
+@pytest.mark.parametrize("q,bits", [(0.5, 8), (0.9, 4), (0.25, 2)])
+def test_slot_quant_kernels_match_reference_quantizer(q, bits):
+    """Radix-select statistics + fused binning == extensions/quantization applied to every client's materialised payload,
+    including tensors whose dead filter taps (structural zeros) are not stored in the slot layout."""
+    from msrflute_b200.extensions.quantization import quant
+    from msrflute_b200.ops import arena_ops
+    torch.manual_seed(3)
+    S = 3
+    # slot row: tensor A (1000 stored of 1000), tensor B (640 stored of 1500: 860 elided zeros), tensor C (33 of 33)
+    offs, stored, total = [0, 1024, 1664], [1000, 640, 33], [1000, 1500, 33]
+    Pc = 1728
+    segs = torch.tensor([[o, n, t] for o, n, t in zip(offs, stored, total)], dtype=torch.int64, device="cuda")
+    blk = torch.full((Pc // 32,), -1, dtype=torch.int16)
+    for t, (o, n) in enumerate(zip(offs, stored)):
+        blk[o // 32:(o + n + 31) // 32] = t
+    blk = blk.cuda()
+    wg = torch.zeros(Pc, device="cuda")
+    W = torch.zeros(S, Pc, device="cuda")
+    for o, n in zip(offs, stored):
+        wg[o:o + n] = torch.randn(n, device="cuda")
+        W[:, o:o + n] = wg[o:o + n] + torch.randn(S, n, device="cuda") * torch.rand(S, 1, device="cuda")
+    coef = torch.tensor([1.0, 0.0, 2.5], device="cuda")
+    params = arena_ops.slot_quant_stats(W, wg, segs, q, bits)
+    acc = torch.zeros(Pc, device="cuda")
+    arena_ops.slot_quant_gather(acc, W, wg, coef, params, blk, bits)
+    want = torch.zeros(Pc, device="cuda")
+    for s in range(S):
+        c = float(coef[s])
+        if c == 0:
+            continue
+        for o, n, t in zip(offs, stored, total):
+            g = c * torch.cat([wg[o:o + n] - W[s, o:o + n], torch.zeros(t - n, device="cuda")])
+            quant.quantize_tensor_(g, bits, q)
+            want[o:o + n] += g[:n]
+            assert float(g[n:].abs().max()) == 0.0 if t > n else True
+    assert torch.allclose(acc, want, atol=1e-5, rtol=1e-4), float((acc - want).abs().max())
+
+
+def test_engine_quantized_gather_matches_generic_path():
+    """BASELINE config #4's algorithmic setting (DGA + gradient quantization) on the engine == the generic path."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    def patch(raw):
+        raw["strategy"] = "DGA"
+        raw["server_config"]["aggregate_median"] = "mean"
+        raw["client_config"]["quant_thresh"] = 0.5
+        raw["client_config"]["quant_bits"] = 6
+        raw["client_config"]["quant_anneal"] = 1.0
+        raw["client_config"]["data_config"]["train"]["batch_size"] = 4096
+
+    server, worker, comm = _build("cv_lr_mnist", patch)
+    assert worker.engine is not None and worker.engine.supports(worker.config)
+    server.begin_training()
+    from msrflute_b200.parallel.arena import module_arena
+    w0 = module_arena(server.worker_trainer.model)[0].flat.clone()
+    ids = [1, 2, 9]
+    worker.set_weights(w0)
+    worker.accumulator().zero_()
+    worker.engine.train_clients(ids, 0.05, 0, worker.weight_buffer(), worker.accumulator())
+    acc_e = worker.accumulator().clone()
+    worker.accumulator().zero_()
+    eng, worker.engine = worker.engine, None
+    worker.train_clients(ids, (0.05, None, 0), fused=True)
+    acc_g = worker.accumulator().clone()
+    worker.engine = eng
+    server.end_training()
+    # identical statistics up to float rounding of (w_global - w_local): allow a handful of boundary elements to land
+    # in the neighbouring bin
+    diff = (acc_e - acc_g).abs()
+    assert float(diff.max()) < 2e-3 and float((diff > 1e-6).float().mean()) < 0.01, (float(diff.max()),)
+    assert float(acc_e.norm()) > 0
