@@ -251,7 +251,8 @@ class Client:
             for g in optimizer.param_groups:
                 g.pop("initial_lr", None)
             trainer.lr_scheduler = make_lr_scheduler(annealing_config, optimizer)
-        trainer.step_fn = ctx.graphed
+        from . import graphed as _graphed
+        _graphed.attach(ctx, trainer, client_config)
 
         assert "desired_max_samples" in data_config, "Missing 'desired_max_samples' entry in data config parameter"
         desired_max_samples = data_config["desired_max_samples"]

@@ -36,6 +36,8 @@
 #include <cudaTypedefs.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
+#include <algorithm>
+#include <queue>
 #include <vector>
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -165,24 +167,42 @@ __device__ __forceinline__ void seg_allreduce2(float (&a)[16], float (&b)[16], i
   }
 }
 
+// Per-CTA pipeline state shared by the per-launch kernel and the persistent step kernel: the TMA -> MMA ring keeps
+// running across tiles (stage / parity derive from a running iteration count), the accumulator barrier flips once per tile.
+struct TileCtx {
+  uint8_t* smem;             // ring: kStages x stage_bytes
+  float* scratch;
+  uint64_t* full_bar; uint64_t* empty_bar;
+  uint64_t* acc_bar;         // [nbuf] accumulator ready (MMA -> epilogue)
+  uint64_t* acc_free;        // [nbuf] accumulator drained (epilogue -> MMA), nbuf == 2 only
+  int nbuf, acc_stride;      // TMEM accumulators per CTA and their distance in columns
+  uint32_t tmem_base;
+  int kStages, stage_bytes;
+  uint32_t it_base;          // ring iterations consumed by earlier tiles of this CTA
+  uint32_t acc_phase;        // tiles with work done by this CTA so far (parity of acc_bar)
+};
+
+// One 128 x TN output tile (bx = row tile / class / k-split, by = column tile, slot).  Returns the number of ring
+// iterations it consumed (identical for every thread of the CTA).
 template <int EPI>
-__global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_constant__ GemmP p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int stage_bytes = A_BYTES + p.TN * 128;
-  const int kStages = p.stages;
-  float* scratch = reinterpret_cast<float*>(smem + kStages * stage_bytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes + SCRATCH_BYTES);
-  uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* acc_bar = empty_bar + kMaxStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_bar + 1);
+__device__ __forceinline__ int gemm_tile(const GemmP& p, const int bx, const int by, const int slot, const TileCtx& c) {
+  uint8_t* const smem = c.smem;
+  const int stage_bytes = c.stage_bytes;
+  const int kStages = c.kStages;
+  float* const scratch = c.scratch;
+  uint64_t* const full_bar = c.full_bar;
+  uint64_t* const empty_bar = c.empty_bar;
+  const int abuf = static_cast<int>(c.acc_phase % static_cast<uint32_t>(c.nbuf));
+  const uint32_t aphase = (c.acc_phase / static_cast<uint32_t>(c.nbuf)) & 1u;
+  uint64_t* const acc_bar = c.acc_bar + abuf;
+  const uint32_t tmem_base = c.tmem_base + static_cast<uint32_t>(abuf * c.acc_stride);
+  const uint32_t it_base = c.it_base;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = blockIdx.z;
-  const int n0 = blockIdx.y * p.TN;
+  const int n0 = by * p.TN;
 
   // ---- tile decode -------------------------------------------------------------------------------------------------
-  int cls = 0, tile = blockIdx.x, tap0 = 0, nt = p.ntaps;
+  int cls = 0, tile = bx, tap0 = 0, nt = p.ntaps;
   int rb = 0, ks = 0;                       // wgrad: row block, k split
   if (p.mode == WGRAD) {
     rb = tile / p.ksplit;
@@ -210,27 +230,6 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
     total_its = nt * ((p.Cred + 31) / 32);
   }
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar + s, 1);
-      mbar_init(empty_bar + s, 1);
-    }
-    mbar_init(acc_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0 && lane < 5) prefetch_tmap(p.maps + lane);
-  if (warp == 1) tmem_alloc(tmem_ptr, static_cast<uint32_t>(p.TN * p.nacc));
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) ran while the
-  // previous kernel of the chain was still executing.  Wait for it to complete (its writes are visible afterwards),
-  // THEN let the next kernel start its own prologue — releasing only after the wait means at most two kernels of the
-  // chain are ever co-resident, and every CTA of this grid is already resident when the successor's CTAs arrive.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
   if (warp == 0) {
     // =============================================================================================== TMA producer
     if (lane == 0 && total_its > 0) {
@@ -242,8 +241,9 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
         for (int i = 0; i < 4; ++i) nA += (rb * TM + 32 * i < p.Kw) ? 1 : 0;
         const uint32_t tx = static_cast<uint32_t>((nA + p.TN / 32) * BLK_BYTES);
         for (int pc = pc_begin; pc < pc_end; ++pc, ++it) {
-          const int s = it % kStages;
-          mbar_wait(empty_bar + s, ((it / kStages) & 1) ^ 1);
+          const uint32_t gi = it_base + static_cast<uint32_t>(it);
+          const int s = static_cast<int>(gi % kStages);
+          mbar_wait(empty_bar + s, ((gi / kStages) & 1) ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + A_BYTES;
           int kb0, ky0;
@@ -268,8 +268,9 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
           const CUtensorMap* mapA = p.maps + p.tap_map[t];
           const int cx = p.tap_dx[t], cy = y0 + p.tap_dy[t], wt = p.tap_w[t];
           for (int c0 = 0; c0 < p.Cred; c0 += 32, ++it) {
-            const int s = it % kStages;
-            mbar_wait(empty_bar + s, ((it / kStages) & 1) ^ 1);
+            const uint32_t gi = it_base + static_cast<uint32_t>(it);
+            const int s = static_cast<int>(gi % kStages);
+            mbar_wait(empty_bar + s, ((gi / kStages) & 1) ^ 1);
             uint8_t* sa = smem + s * stage_bytes;
             uint8_t* sb = sa + A_BYTES;
             if (p.dbg & 2) { mbar_expect_tx(full_bar + s, 0); continue; }
@@ -291,9 +292,14 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
       const bool a_mn = p.mode == WGRAD, b_mn = p.mode != FPROP;
       const uint32_t idesc = make_idesc_fmt(TM, p.TN, 2u) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
       const uint64_t a_step = static_cast<uint64_t>(p.a_kstep), b_step = static_cast<uint64_t>(p.b_kstep);
+      if (c.nbuf > 1) {                                   // the epilogue of two tiles ago has drained this accumulator
+        mbar_wait(c.acc_free + abuf, aphase ^ 1u);
+        tc_fence_after();
+      }
       for (int it = 0; it < total_its; ++it) {
-        const int s = it % kStages;
-        mbar_wait(full_bar + s, (it / kStages) & 1);
+        const uint32_t gi = it_base + static_cast<uint32_t>(it);
+        const int s = static_cast<int>(gi % kStages);
+        mbar_wait(full_bar + s, (gi / kStages) & 1);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
         const uint64_t adesc = make_desc(a_addr, p.a_lbo, p.a_sbo, p.a_layout);
@@ -312,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
     }
   } else if (total_its > 0) {
     // =============================================================================================== epilogue
-    mbar_wait(acc_bar, 0);
+    mbar_wait(acc_bar, aphase);
     tc_fence_after();
     const int q = warp & 3;                          // TMEM lane quadrant this warp may read
     const int r = q * 32 + lane;                     // tile row of this thread
@@ -593,11 +599,58 @@ __global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_const
       }
     }
     tc_fence_before();
+    if (c.nbuf > 1) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(c.acc_free + abuf);
+    }
   }
+  return total_its;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 2) sn_gemm_kernel(const __grid_constant__ GemmP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  TileCtx c;
+  c.smem = smem;
+  c.stage_bytes = A_BYTES + p.TN * 128;
+  c.kStages = p.stages;
+  c.scratch = reinterpret_cast<float*>(smem + c.kStages * c.stage_bytes);
+  c.full_bar = reinterpret_cast<uint64_t*>(smem + c.kStages * c.stage_bytes + SCRATCH_BYTES);
+  c.empty_bar = c.full_bar + kMaxStages;
+  c.acc_bar = c.empty_bar + kMaxStages;
+  c.acc_free = c.acc_bar;
+  c.nbuf = 1;
+  c.acc_stride = 0;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(c.acc_bar + 1);
+  c.it_base = 0;
+  c.acc_phase = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < c.kStages; ++s) {
+      mbar_init(c.full_bar + s, 1);
+      mbar_init(c.empty_bar + s, 1);
+    }
+    mbar_init(c.acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane < 5) prefetch_tmap(p.maps + lane);
+  if (warp == 1) tmem_alloc(tmem_ptr, static_cast<uint32_t>(p.TN * p.nacc));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tmem_base = *tmem_ptr;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) ran while the
+  // previous kernel of the chain was still executing.  Wait for it to complete (its writes are visible afterwards),
+  // THEN let the next kernel start its own prologue — releasing only after the wait means at most two kernels of the
+  // chain are ever co-resident, and every CTA of this grid is already resident when the successor's CTAs arrive.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  gemm_tile<EPI>(p, blockIdx.x, blockIdx.y, blockIdx.z, c);
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.TN * p.nacc));
+    tmem_dealloc(c.tmem_base, static_cast<uint32_t>(p.TN * p.nacc));
   }
 }
 
@@ -764,11 +817,11 @@ struct GnBwdP {
   const float* Warena; float* Garena; long long arena_stride, gamma_off, beta_off;
   int N, B, H, W, C;
 };
-__global__ void __launch_bounds__(128) sn_gn_bwd_kernel(const GnBwdP p, const int PS) {
+// t = global thread index (whole warps share a block): used by the stand-alone kernel and by the persistent step kernel
+__device__ __forceinline__ void gn_bwd_block(const GnBwdP& p, const int PS, const long long t) {
   // lane = pixel lane * (32 / PS) + group: PS (power of two <= 8, <= H*W) lanes share one (image, group) and split its
   // pixels; for a fixed pixel lane the warp's 32 / PS groups are adjacent channels (one full 32-byte sector at PS = 8)
   const int G2 = p.C / 2;
-  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, gs = 32 / PS;
   const int pl = lane / gs;
   const long long idx = (t >> 5) * gs + (lane - pl * gs);
@@ -826,6 +879,9 @@ __global__ void __launch_bounds__(128) sn_gn_bwd_kernel(const GnBwdP p, const in
     *reinterpret_cast<float2*>(p.dz + o) = make_float2(st.y * (d.x * ga - Bm - x0 * A), st.y * (d.y * ga - Bm - x1 * A));
   }
 }
+__global__ void __launch_bounds__(128) sn_gn_bwd_kernel(const GnBwdP p, const int PS) {
+  gn_bwd_block(p, PS, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x);
+}
 
 // softmax cross-entropy (mean over the slot's batch) forward + backward, bias gradient, per-slot loss accumulation
 struct CeP {
@@ -860,6 +916,150 @@ __global__ void __launch_bounds__(256) sn_ce_kernel(const CeP p) {
     atomicAdd(Gs + j, d);
   }
   if (tid == 0) atomicAdd(p.loss + slot, (logf(s) + m - x[label]) * inv_b);
+}
+
+// ============================================================================================ persistent step kernel
+// One cooperative launch runs a whole dependency-ordered range of the program (the 20 forward convolutions, or the
+// whole backward pass from the classifier to layer1): the host groups ops into PHASES (an op's phase is one more than
+// the latest phase that produced one of its inputs), cuts every op into its 128 x TN tiles, balances the tiles of a
+// phase over the resident CTAs (longest-processing-time first) and uploads the per-CTA work lists.  Inside the kernel a
+// CTA keeps its TMEM allocation, mbarrier ring and tensor-map cache across tiles and meets the other CTAs at a grid
+// barrier between phases — ~1.5 us instead of a kernel boundary, and independent ops (down-sample branch next to conv1,
+// every weight gradient next to the data-gradient chain) share a phase.  Replaces ~70 dependent launches per local step.
+constexpr int kMegaStages = 3;
+constexpr int kMegaStageBytes = A_BYTES + 64 * 128;
+constexpr int kMaxPhaseOps = 6;
+struct MegaOp {
+  int kind;                  // 0 gemm, 4 GroupNorm backward
+  int ps;                    // gn: pixel lanes
+  int pad[2];
+  GemmP g;
+  GnBwdP n;
+};
+struct MegaP {
+  const MegaOp* ops;
+  const int* phase_ops;      // [nphases][kMaxPhaseOps] op indices of the phase (-1: unused)
+  const int4* items;         // {op slot inside the phase, bx, by, slot}
+  const int* cta_start;      // [nphases][ncta + 1] offsets into items
+  int nphases, ncta;
+  unsigned* bar;             // [0] phase barrier, [1] exit counter (the last CTA out resets both)
+};
+constexpr int kMegaOpBytes = ((static_cast<int>(sizeof(MegaOp)) + 15) / 16) * 16;
+constexpr int kMegaSmem = kMegaStages * kMegaStageBytes + SCRATCH_BYTES + (2 * kMaxStages + 4) * 8 + 16 +
+                          kMaxPhaseOps * kMegaOpBytes + 1024;
+constexpr int kEpiThreads = 128;
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __maxnreg__(160) sn_mega_kernel(const __grid_constant__ MegaP mp) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  TileCtx c;
+  c.smem = smem;
+  c.stage_bytes = kMegaStageBytes;
+  c.kStages = kMegaStages;
+  c.scratch = reinterpret_cast<float*>(smem + kMegaStages * kMegaStageBytes);
+  c.full_bar = reinterpret_cast<uint64_t*>(smem + kMegaStages * kMegaStageBytes + SCRATCH_BYTES);
+  c.empty_bar = c.full_bar + kMaxStages;
+  c.acc_bar = c.empty_bar + kMaxStages;          // [2]
+  c.acc_free = c.acc_bar + 2;                    // [2]
+  c.nbuf = 2;
+  c.acc_stride = 64;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(c.acc_free + 2);
+  uint8_t* optab = reinterpret_cast<uint8_t*>(tmem_ptr) + 16;     // the phase's op records
+  c.it_base = 0;
+  c.acc_phase = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMegaStages; ++s) {
+      mbar_init(c.full_bar + s, 1);
+      mbar_init(c.empty_bar + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(c.acc_bar + b, 1);
+      mbar_init(c.acc_free + b, kEpiThreads / 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 128u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tmem_base = *tmem_ptr;
+
+  const unsigned G = gridDim.x;
+  for (int ph = 0; ph < mp.nphases; ++ph) {
+    // ---- this phase's op records -> shared memory (every role reads its parameters from there) -----------------------
+    const int* pops = mp.phase_ops + ph * kMaxPhaseOps;
+    for (int k = 0; k < kMaxPhaseOps; ++k) {
+      const int oi = __ldg(pops + k);
+      if (oi < 0) break;
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(mp.ops + oi);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(optab + k * kMegaOpBytes);
+      for (int w = threadIdx.x; w < static_cast<int>(sizeof(MegaOp) / 4); w += kThreads) dst[w] = __ldg(src + w);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int k = lane / 5, m = lane - k * 5;
+      if (k < kMaxPhaseOps && __ldg(pops + k) >= 0) {
+        const MegaOp* o = reinterpret_cast<const MegaOp*>(optab + k * kMegaOpBytes);
+        if (o->kind == 0) prefetch_tmap(o->g.maps + m);
+      }
+    }
+    const int* cs = mp.cta_start + static_cast<long long>(ph) * (mp.ncta + 1) + blockIdx.x;
+    const int i0 = __ldg(cs), i1 = __ldg(cs + 1);
+    // Roles walk the CTA's tile list independently: the producer runs ahead as far as the ring allows, the MMA thread
+    // as far as the two accumulators allow, the epilogue warps drain behind them.
+    for (int i = i0; i < i1; ++i) {
+      const int4 item = __ldg(mp.items + i);
+      const MegaOp* o = reinterpret_cast<const MegaOp*>(optab + item.x * kMegaOpBytes);
+      if (o->kind == 0) {
+        const GemmP& p = o->g;
+        int its;
+        switch (p.epi) {
+          case E_STORE: its = gemm_tile<E_STORE>(p, item.y, item.z, item.w, c); break;
+          case E_GNFWD: its = gemm_tile<E_GNFWD>(p, item.y, item.z, item.w, c); break;
+          case E_GNBWD: its = gemm_tile<E_GNBWD>(p, item.y, item.z, item.w, c); break;
+          default:      its = gemm_tile<E_WGRAD>(p, item.y, item.z, item.w, c); break;
+        }
+        c.it_base += static_cast<uint32_t>(its);
+        c.acc_phase += its > 0 ? 1u : 0u;
+      } else if (warp >= 2) {
+        gn_bwd_block(o->n, o->ps, static_cast<long long>(item.y) * kEpiThreads + (threadIdx.x - 64));
+      }
+    }
+    // global results of this phase become visible to the async proxy (TMA reads of the next phase) of every CTA
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (ph + 1 < mp.nphases) {
+      // ---- grid barrier --------------------------------------------------------------------------------------------
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(mp.bar, 1u);
+        const unsigned target = G * static_cast<unsigned>(ph + 1);
+        while (ld_acquire_u32(mp.bar) < target) { }
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(mp.bar + 1, 1u);
+    if (prev == G - 1) {               // every CTA has left its last barrier: safe to re-arm for the next launch
+      mp.bar[0] = 0u;
+      mp.bar[1] = 0u;
+      __threadfence();
+    }
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(c.tmem_base, 128u);
+  }
 }
 
 // ====================================================================================================== host side
@@ -1095,6 +1295,16 @@ class Program {
     bool side_used = false;
     int64_t n = 0;
     for (int64_t i = begin; i < end; ++i) {
+      if (use_mega_) {
+        const Mega* hit = nullptr;
+        for (const auto& m : megas_) if (m.begin == i && m.end <= end) hit = &m;
+        if (hit != nullptr) {
+          launch_mega(*hit, main_stream);
+          i = hit->end - 1;
+          ++n;
+          continue;
+        }
+      }
       const Op& op = ops_[i];
       cudaStream_t stream = main_stream;
       if (use_side_ && op.side) {
@@ -1147,8 +1357,155 @@ class Program {
 
   int64_t num_ops() const { return static_cast<int64_t>(ops_.size()); }
   void set_pdl(bool on) { use_pdl_ = on; }
+  void set_mega(bool on) { use_mega_ = on; }
+
+  // Fuse ops [begin, end) (GEMMs and stand-alone GroupNorm backward only) into ONE persistent cooperative launch.
+  // phases[i] = dependency level of op begin + i (ops of one phase are mutually independent).  Returns the number of
+  // resident CTAs the work was balanced over.
+  int64_t add_mega(int64_t begin, int64_t end, std::vector<int> phases, int64_t ctas_per_sm) {
+    TORCH_CHECK(finalized_, "finalize() first");
+    TORCH_CHECK(begin >= 0 && end <= static_cast<int64_t>(ops_.size()) && begin < end &&
+                static_cast<int64_t>(phases.size()) == end - begin, "add_mega: bad range");
+    FLUTE_CUDA_CHECK(cudaFuncSetAttribute(sn_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMegaSmem));
+    FLUTE_CUDA_CHECK(cudaFuncSetAttribute(sn_mega_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
+    int dev = 0, sms = 0, occ = 0;
+    FLUTE_CUDA_CHECK(cudaGetDevice(&dev));
+    FLUTE_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FLUTE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sn_mega_kernel, kThreads, kMegaSmem));
+    TORCH_CHECK(occ >= 1, "persistent step kernel does not fit on an SM");
+    max_occ_ = occ;
+    if (ctas_per_sm > 0) occ = static_cast<int>(ctas_per_sm);    // explicit request (the cooperative launch validates it)
+    const int ncta = occ * sms;
+    int nph = 0;
+    for (int v : phases) { TORCH_CHECK(v >= 0, "negative phase"); nph = std::max(nph, v + 1); }
+
+    struct Item { int op, bx, by, slot; float cost; };
+    std::vector<int> phase_ops(static_cast<size_t>(nph) * kMaxPhaseOps, -1);
+    std::vector<int> phase_nops(nph, 0);
+    std::vector<MegaOp> mops;
+    std::vector<std::vector<Item>> by_phase(nph);
+    for (int64_t i = begin; i < end; ++i) {
+      const Op& op = ops_[i];
+      MegaOp mo{};
+      const int ph_i = phases[i - begin];
+      TORCH_CHECK(phase_nops[ph_i] < kMaxPhaseOps, "add_mega: more than ", kMaxPhaseOps, " ops in phase ", ph_i);
+      const int oi = phase_nops[ph_i]++;                      // slot inside the phase's op table
+      phase_ops[static_cast<size_t>(ph_i) * kMaxPhaseOps + oi] = static_cast<int>(mops.size());
+      auto& dst = by_phase[ph_i];
+      if (op.kind == 0) {
+        mo.kind = 0;
+        mo.g = op.g;
+        mo.g.nacc = 1;
+        TORCH_CHECK(mo.g.TN <= 64, "persistent step kernel: TN <= 64");
+        const GemmP& g = mo.g;
+        for (unsigned z = 0; z < op.grid.z; ++z)
+          for (unsigned y = 0; y < op.grid.y; ++y)
+            for (unsigned x = 0; x < op.grid.x; ++x) {
+              int its;
+              if (g.mode == WGRAD) {
+                const int per = (g.kchunks + g.ksplit - 1) / g.ksplit;
+                const int ks = static_cast<int>(x) % g.ksplit;
+                its = std::max(0, std::min(g.kchunks, ks * per + per) - ks * per);
+              } else {
+                const int nt = g.ncls == 4 ? g.cls_nt[x / g.row_tiles] : g.ntaps;
+                its = nt * ((g.Cred + 31) / 32);
+              }
+              const float fixed = g.epi == E_WGRAD ? 16.f : (g.epi == E_STORE ? 10.f : 13.f);
+              dst.push_back({oi, static_cast<int>(x), static_cast<int>(y), static_cast<int>(z), fixed + static_cast<float>(its)});
+            }
+      } else if (op.kind == 4) {
+        mo.kind = 4;
+        mo.n = op.gn;
+        const int hw = op.gn.H * op.gn.W;
+        mo.ps = hw >= 8 ? 8 : hw;
+        const long long groups = static_cast<long long>(op.gn.N) * (op.gn.C / 2);
+        const long long warps = (groups + (32 / mo.ps) - 1) / (32 / mo.ps);
+        const int blocks = static_cast<int>((warps + (kEpiThreads / 32) - 1) / (kEpiThreads / 32));
+        for (int b = 0; b < blocks; ++b) dst.push_back({oi, b, 0, 0, 8.f + 0.5f * static_cast<float>(hw / mo.ps)});
+      } else {
+        TORCH_CHECK(false, "add_mega: op ", i, " of kind ", op.kind, " cannot run inside the persistent kernel");
+      }
+      mops.push_back(mo);
+    }
+    // longest-processing-time-first balancing of every phase over the resident CTAs
+    std::vector<int4> items;
+    std::vector<int> cta_start(static_cast<size_t>(nph) * (ncta + 1), 0);
+    float crit = 0.f;
+    for (int ph = 0; ph < nph; ++ph) {
+      auto& v = by_phase[ph];
+      std::stable_sort(v.begin(), v.end(), [](const Item& a, const Item& b) { return a.cost > b.cost; });
+      std::vector<std::vector<int>> mine(ncta);
+      std::priority_queue<std::pair<float, int>, std::vector<std::pair<float, int>>, std::greater<std::pair<float, int>>> pq;
+      for (int cta = 0; cta < ncta; ++cta) pq.push({0.f, cta});
+      float worst = 0.f;
+      for (size_t k = 0; k < v.size(); ++k) {
+        auto top = pq.top(); pq.pop();
+        mine[top.second].push_back(static_cast<int>(k));
+        top.first += v[k].cost;
+        worst = std::max(worst, top.first);
+        pq.push(top);
+      }
+      crit += worst;
+      for (int cta = 0; cta < ncta; ++cta) {
+        // keep tiles of the same op adjacent so the shared op copy is reloaded as rarely as possible
+        std::stable_sort(mine[cta].begin(), mine[cta].end(), [&](int a, int b) { return v[a].op < v[b].op; });
+        cta_start[static_cast<size_t>(ph) * (ncta + 1) + cta] = static_cast<int>(items.size());
+        for (int k : mine[cta]) items.push_back(make_int4(v[k].op, v[k].bx, v[k].by, v[k].slot));
+      }
+      cta_start[static_cast<size_t>(ph) * (ncta + 1) + ncta] = static_cast<int>(items.size());
+    }
+    Mega m;
+    m.begin = begin; m.end = end; m.grid = ncta; m.nphases = nph; m.est_cost = crit;
+    auto u8 = torch::TensorOptions().dtype(torch::kUInt8).device(torch::kCUDA);
+    m.ops_dev = torch::empty({static_cast<int64_t>(mops.size() * sizeof(MegaOp))}, u8);
+    m.items_dev = torch::empty({static_cast<int64_t>(std::max<size_t>(1, items.size()) * sizeof(int4))}, u8);
+    m.cta_dev = torch::empty({static_cast<int64_t>(cta_start.size() * sizeof(int))}, u8);
+    m.pops_dev = torch::empty({static_cast<int64_t>(phase_ops.size() * sizeof(int))}, u8);
+    FLUTE_CUDA_CHECK(cudaMemcpy(m.pops_dev.data_ptr(), phase_ops.data(), phase_ops.size() * sizeof(int), cudaMemcpyHostToDevice));
+    m.p.phase_ops = reinterpret_cast<const int*>(m.pops_dev.data_ptr());
+    m.bar_dev = torch::zeros({64}, u8);
+    FLUTE_CUDA_CHECK(cudaMemcpy(m.ops_dev.data_ptr(), mops.data(), mops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice));
+    FLUTE_CUDA_CHECK(cudaMemcpy(m.items_dev.data_ptr(), items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    FLUTE_CUDA_CHECK(cudaMemcpy(m.cta_dev.data_ptr(), cta_start.data(), cta_start.size() * sizeof(int), cudaMemcpyHostToDevice));
+    m.p.ops = reinterpret_cast<const MegaOp*>(m.ops_dev.data_ptr());
+    m.p.items = reinterpret_cast<const int4*>(m.items_dev.data_ptr());
+    m.p.cta_start = reinterpret_cast<const int*>(m.cta_dev.data_ptr());
+    m.p.nphases = nph; m.p.ncta = ncta;
+    m.p.bar = reinterpret_cast<unsigned*>(m.bar_dev.data_ptr());
+    megas_.push_back(m);
+    use_mega_ = true;
+    return ncta;
+  }
+  // {begin, end, phases, ctas, estimated critical path in ring iterations} of every fused range
+  std::vector<std::vector<double>> mega_info() const {
+    std::vector<std::vector<double>> r;
+    for (const auto& m : megas_)
+      r.push_back({static_cast<double>(m.begin), static_cast<double>(m.end), static_cast<double>(m.nphases),
+                   static_cast<double>(m.grid), static_cast<double>(m.est_cost), static_cast<double>(max_occ_),
+                   static_cast<double>(kMegaSmem)});
+    return r;
+  }
 
  private:
+  struct Mega {
+    int64_t begin, end; int grid, nphases; float est_cost;
+    torch::Tensor ops_dev, items_dev, cta_dev, bar_dev, pops_dev;
+    MegaP p;
+  };
+  void launch_mega(const Mega& m, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(m.grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = static_cast<size_t>(kMegaSmem);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the phase barrier cannot deadlock
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FLUTE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sn_mega_kernel, m.p));
+  }
   void launch_gemm(const Op& op, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = op.grid;
@@ -1180,6 +1537,9 @@ class Program {
   bool finalized_ = false;
   bool use_side_ = false;
   bool use_pdl_ = true;
+  bool use_mega_ = false;
+  int max_occ_ = 0;
+  std::vector<Mega> megas_;
   cudaStream_t side_stream_ = nullptr;
   cudaEvent_t join_event_ = nullptr;
   std::vector<cudaEvent_t> fork_events_;
@@ -1187,7 +1547,20 @@ class Program {
 
 }  // namespace sn
 
+// resource usage / occupancy of the persistent kernel (diagnostics)
+static std::vector<int64_t> slotnet_mega_attrs(int64_t smem) {
+  cudaFuncAttributes a{};
+  FLUTE_CUDA_CHECK(cudaFuncGetAttributes(&a, sn::sn_mega_kernel));
+  FLUTE_CUDA_CHECK(cudaFuncSetAttribute(sn::sn_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sn::kMegaSmem));
+  int occ = 0;
+  FLUTE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sn::sn_mega_kernel, sn::kThreads,
+                                                                static_cast<size_t>(smem > 0 ? smem : sn::kMegaSmem)));
+  return {a.numRegs, static_cast<int64_t>(a.sharedSizeBytes), static_cast<int64_t>(a.localSizeBytes),
+          a.maxThreadsPerBlock, occ, sn::kMegaSmem};
+}
+
 void bind_slotnet(py::module_& m) {
+  m.def("slotnet_mega_attrs", &slotnet_mega_attrs, py::arg("smem") = 0);
   py::class_<sn::Program>(m, "SlotProgram")
       .def(py::init<>())
       .def("add_map", &sn::Program::add_map, py::arg("ptr"), py::arg("dims"), py::arg("strides"), py::arg("box"),
@@ -1202,6 +1575,9 @@ void bind_slotnet(py::module_& m) {
       .def("run", &sn::Program::run, py::arg("begin") = 0, py::arg("end") = -1)
       .def("set_side_stream", &sn::Program::set_side_stream)
       .def("set_pdl", &sn::Program::set_pdl)
+      .def("set_mega", &sn::Program::set_mega)
+      .def("add_mega", &sn::Program::add_mega, py::arg("begin"), py::arg("end"), py::arg("phases"), py::arg("ctas_per_sm") = 0)
+      .def("mega_info", &sn::Program::mega_info)
       .def("num_ops", &sn::Program::num_ops);
 }
 

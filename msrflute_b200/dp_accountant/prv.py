@@ -45,8 +45,11 @@ class PrivacyRandomVariableTruncated:
 
     def mean(self) -> float:
         # E[Y] = t_max − ∫ CDF over the truncated support, integrated on a grid refined around 0
+        # point masses (Laplace / pure-DP losses) are bracketed by a 2e-12 wide cell so the midpoint rule places them exactly
+        atoms = np.asarray(getattr(self.prv, "atoms", lambda: [])(), dtype=np.float64)
+        around = np.concatenate([atoms - 1e-12, atoms + 1e-12]) if atoms.size else atoms
         pts = np.unique(np.clip(np.concatenate([[self.t_min], -np.logspace(-5, np.log10(max(-self.t_min, 1e-4)), 200)[::-1], [0.0],
-                                                np.logspace(-5, np.log10(max(self.t_max, 1e-4)), 200), [self.t_max]]),
+                                                np.logspace(-5, np.log10(max(self.t_max, 1e-4)), 200), [self.t_max], around]),
                                 self.t_min, self.t_max))
         m = 0.0
         for a, b in zip(pts[:-1], pts[1:]):
@@ -82,6 +85,9 @@ class LaplaceMechanism(PrivacyRandomVariable):
         mid = 0.5 * np.exp(0.5 * (np.clip(t, -self.mu, self.mu) - self.mu))
         return np.where(t >= self.mu, 1.0, np.where(t <= -self.mu, 0.0, mid))
 
+    def atoms(self):
+        return [-self.mu, self.mu]
+
     def rdp(self, alpha):
         mu = self.mu
         if alpha == 1:
@@ -99,6 +105,9 @@ class PureDPMechanism(PrivacyRandomVariable):
     def cdf(self, t):
         t = np.asarray(t, dtype=np.float64)
         return np.where(t < -self.eps, 0.0, np.where(t < self.eps, 1.0 / (1.0 + np.exp(self.eps)), 1.0))
+
+    def atoms(self):
+        return [-self.eps, self.eps]
 
     def mean(self):
         e = self.eps

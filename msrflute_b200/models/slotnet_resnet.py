@@ -85,6 +85,7 @@ class SlotProgramBuilder:
         self.prog = ext.SlotProgram()
         self._keep = []
         self.op_names = []           # one label per program op (tools/profile_slotnet.py)
+        self.op_rw = {}              # op index -> (buffers read, buffers written): phase assignment of the fused kernel
 
     def _buf(self, shape):
         t = torch.zeros(shape, dtype=torch.float32, device=self.dev)
@@ -175,6 +176,7 @@ class SlotProgramBuilder:
                  tap_dx=dx, tap_dy=dy, tap_map=mp, tap_w=list(range(cv.nt)), maps=maps, **geo)
         d.update({k: (v.data_ptr() if torch.is_tensor(v) else v) for k, v in kw.items() if v is not None})
         self.prog.add_gemm(d)
+        self._track([x, kw.get("res")], [kw.get("out"), kw.get("out2"), kw.get("stats") if epi == E_GNFWD else None])
         self._label("fprop {} e{} TN{} grid {}x{}x{} its {}".format(
             cv.name, epi, TN, geo["row_tiles"], math.ceil(cv.Cout / TN), self.S, cv.nt * math.ceil(Cin / 32)))
 
@@ -182,6 +184,27 @@ class SlotProgramBuilder:
         while len(self.op_names) < self.prog.num_ops() - 1:
             self.op_names.append("op")
         self.op_names.append(text)
+
+    def _track(self, reads, writes):
+        """Record the activation buffers the op just added reads / writes (the parameter arena is read-only during a
+        step and the gradient arena only receives commutative atomics: neither orders ops)."""
+        ptr = lambda t: t.data_ptr() if torch.is_tensor(t) else int(t)
+        self.op_rw[self.prog.num_ops() - 1] = ({ptr(t) for t in reads if t is not None},
+                                               {ptr(t) for t in writes if t is not None})
+
+    def phases(self, begin, end):
+        """Dependency level of every op in [begin, end): one more than the latest earlier op it conflicts with
+        (read-after-write, write-after-write or write-after-read on an activation buffer)."""
+        ph = []
+        for i in range(begin, end):
+            ri, wi = self.op_rw[i]
+            lvl = 0
+            for j in range(begin, i):
+                rj, wj = self.op_rw[j]
+                if (wj & ri) or (wj & wi) or (rj & wi):
+                    lvl = max(lvl, ph[j - begin] + 1)
+            ph.append(lvl)
+        return ph
 
     def _dgrad(self, cv, dy_t, epi, **kw):
         """dy_t: gradient wrt the conv output [S,B,Ho,Wo,Cout] → rows = input pixels (per parity class if stride 2)."""
@@ -215,6 +238,7 @@ class SlotProgramBuilder:
             d["b_desc"] = list(self.MN_DESC)
         d.update({k: (v.data_ptr() if torch.is_tensor(v) else v) for k, v in kw.items() if v is not None})
         self.prog.add_gemm(d)
+        self._track([dy_t, kw.get("res"), kw.get("yprev"), kw.get("zprev"), kw.get("stats")], [kw.get("out"), kw.get("out2")])
         self._label("dgrad {} e{} TN{} grid {}x{}x{} its {}".format(
             cv.name, epi, TN, geo["row_tiles"] * extra["ncls"], math.ceil(cv.Cin / TN), self.S,
             max(extra.get("cls_nt", [extra["ntaps"]])) * math.ceil(cv.Cout / 32)))
@@ -242,6 +266,7 @@ class SlotProgramBuilder:
         if self.MN_DESC is not None:
             d["a_desc"], d["b_desc"] = list(self.MN_DESC), list(self.MN_DESC)
         self.prog.add_gemm(d)
+        self._track([x, dy_t], [])
         self._label("wgrad {} TN{} grid {}x{}x{} its {}".format(
             cv.name, TN, row_blocks * ksplit, math.ceil(cv.Cout / TN), self.S, math.ceil(kg["kchunks"] / ksplit)))
 
@@ -380,6 +405,12 @@ class SlotNetResNet(SlotProgramBuilder):
         import os as _os
         self.prog.set_side_stream(_os.environ.get("FLUTE_SLOTNET_SIDE", "1") == "1")
         self.prog.set_pdl(_os.environ.get("FLUTE_SLOTNET_PDL", "1") == "1")
+        # persistent step kernels: the 20 forward GEMMs and the whole backward pass become one cooperative launch each
+        self.fused = _os.environ.get("FLUTE_SLOTNET_FUSED", "1") == "1"
+        if self.fused:
+            cps = int(_os.environ.get("FLUTE_SLOTNET_FUSED_CTAS", "0"))
+            for b, e in ((self.fwd_fuse_begin, self.fwd_fuse_end), (self.bwd_fuse_begin, self.bwd_fuse_end)):
+                self.prog.add_mega(b, e, self.phases(b, e), cps)
         self.n_ops = self.prog.num_ops()
 
     def _gn(self, name):
@@ -399,6 +430,7 @@ class SlotNetResNet(SlotProgramBuilder):
                                pooled=self.pool.data_ptr(), arg=self.arg.data_ptr(), Warena=self.W.data_ptr(),
                                Garena=self.G.data_ptr(), arena_stride=self.P, B=B, eps=self.eps, N=S * B))
         x = self.pool
+        self.fwd_fuse_begin = p.num_ops()
         for blk in self.blocks:
             pre = blk["prefix"]
             self._fprop(blk["c1"], x, E_GNFWD, out=blk["a1"], out2=blk["z1"], stats=blk["st1"], relu=1,
@@ -412,6 +444,7 @@ class SlotNetResNet(SlotProgramBuilder):
                         **self._gn(pre + ".bn2"))
             x = blk["out"]
         self._fprop(fc, x, E_STORE, out=self.logits, bias_off=self.off["net.fc.bias"])
+        self.fwd_fuse_end = p.num_ops()
         p.add_ce(dict(logits=self.logits.data_ptr(), labels=self.labels.data_ptr(), dlogits=self.dlogits.data_ptr(),
                       loss=self.loss.data_ptr(), Garena=self.G.data_ptr(), arena_stride=self.P,
                       bias_off=self.off["net.fc.bias"], B=B, C=fc.Cout, rows=S * B))
@@ -422,6 +455,7 @@ class SlotNetResNet(SlotProgramBuilder):
         blocks = self.blocks
         last = blocks[-1]
         # FC: weight gradient, then data gradient fused with ReLU mask + GroupNorm backward of the last block's bn2
+        self.bwd_fuse_begin = p.num_ops()
         self._wgrad(fc, last["out"], self.dlogits)
         self._dgrad(fc, self.dlogits, E_GNBWD, out=last["dz2"], out2=last["T"], stats=last["st2"], yprev=last["out"],
                     zprev=last["z2"], relu=1, **self._gn(last["prefix"] + ".bn2"))
@@ -449,6 +483,7 @@ class SlotNetResNet(SlotProgramBuilder):
                                   stats=blk["stds"].data_ptr(), dz=blk["dzds"].data_ptr(), Warena=self.W.data_ptr(),
                                   Garena=self.G.data_ptr(), arena_stride=self.P, N=S * B, B=B, H=blk["Ho"], W=blk["Ho"],
                                   C=blk["Cout"]))
+                self._track([blk["T"], blk["zds"], blk["stds"]], [blk["dzds"]])
                 self._wgrad(blk["ds"], x_in, blk["dzds"])
                 ds_half = _Conv(blk["ds"].name, blk["Cin"], blk["Cout"], 1, 1, 1, 0, blk["Ho"], blk["Ho"])
                 ds_half.w_off = blk["ds"].w_off
@@ -460,6 +495,8 @@ class SlotNetResNet(SlotProgramBuilder):
                                   stats=prev["st2"].data_ptr(), tm=prev["T"].data_ptr(), dz=prev["dz2"].data_ptr(),
                                   Warena=self.W.data_ptr(), Garena=self.G.data_ptr(), arena_stride=self.P, N=S * B, B=B,
                                   H=blk["Hi"], W=blk["Hi"], C=blk["Cin"]))
+                self._track([blk["dxm"], blk["dxds"], prev["out"], prev["z2"], prev["st2"]], [prev["T"], prev["dz2"]])
+        self.bwd_fuse_end = p.num_ops()
         p.add_stem(True, dict(self._gn("bn1"), z=self.z_stem.data_ptr(), stats=self.st_stem.data_ptr(),
                               pooled=self.pool.data_ptr(), arg=self.arg.data_ptr(), dpool=self.dpool.data_ptr(),
                               dz=self.dz_stem.data_ptr(), Warena=self.W.data_ptr(), Garena=self.G.data_ptr(),

