@@ -7,6 +7,7 @@ void fused_client_step(torch::Tensor w, torch::Tensor g, torch::Tensor hyper, to
                        bool nesterov, double dampening, bool zero_grad, c10::optional<torch::Tensor> prox_ref,
                        c10::optional<torch::Tensor> prox_mult, c10::optional<torch::Tensor> prox_loss);
 void slot_gather_bcast(torch::Tensor W, torch::Tensor wg_slot, torch::Tensor wg, torch::Tensor map);
+torch::Tensor alpha_dot(torch::Tensor wp, torch::Tensor wg, torch::Tensor gp, torch::Tensor gg, double alpha);
 void slot_pg_sqnorm(torch::Tensor W, torch::Tensor wg_slot, torch::Tensor out);
 void slot_gather_fused(torch::Tensor acc_slot, torch::Tensor W, torch::Tensor wg_slot, torch::Tensor coef,
                        c10::optional<torch::Tensor> sig, c10::optional<torch::Tensor> seed);
@@ -103,6 +104,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         pybind11::arg("prox_ref") = pybind11::none(), pybind11::arg("prox_mult") = pybind11::none(),
         pybind11::arg("prox_loss") = pybind11::none());
   m.def("slot_gather_bcast", &flute::slot_gather_bcast);
+  m.def("alpha_dot", &flute::alpha_dot);
   m.def("slot_pg_sqnorm", &flute::slot_pg_sqnorm);
   m.def("slot_gather_fused", &flute::slot_gather_fused);
   m.def("slot_scatter_acc", &flute::slot_scatter_acc);

@@ -200,4 +200,52 @@ void dead_coord_noise(torch::Tensor acc, torch::Tensor idx, torch::Tensor sig2_s
   FLUTE_CUDA_CHECK(cudaGetLastError());
 }
 
+// ---- personalization mixing weight (/root/reference/utils/utils.py:605-617) -------------------------------
+// out[0] += sum_i (wp_i - wg_i) * (alpha * gp_i + (1 - alpha) * gg_i): ONE pass over the four flat arenas instead of a
+// dot product per parameter tensor plus two concatenations.
+namespace gk {
+__global__ void __launch_bounds__(256) alpha_dot_kernel(const float* __restrict__ wp, const float* __restrict__ wg,
+                                                        const float* __restrict__ gp, const float* __restrict__ gg,
+                                                        long long n, float alpha, double* __restrict__ out) {
+  double acc = 0.0;
+  const long long n4 = n >> 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(wp)[i], b = reinterpret_cast<const float4*>(wg)[i];
+    const float4 c = reinterpret_cast<const float4*>(gp)[i], d = reinterpret_cast<const float4*>(gg)[i];
+    float s = (a.x - b.x) * (alpha * c.x + (1.f - alpha) * d.x);
+    s += (a.y - b.y) * (alpha * c.y + (1.f - alpha) * d.y);
+    s += (a.z - b.z) * (alpha * c.z + (1.f - alpha) * d.z);
+    s += (a.w - b.w) * (alpha * c.w + (1.f - alpha) * d.w);
+    acc += static_cast<double>(s);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 << 2; i < n; ++i) acc += static_cast<double>((wp[i] - wg[i]) * (alpha * gp[i] + (1.f - alpha) * gg[i]));
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out, t);
+  }
+}
+}  // namespace gk
+
+torch::Tensor alpha_dot(torch::Tensor wp, torch::Tensor wg, torch::Tensor gp, torch::Tensor gg, double alpha) {
+  const int64_t n = wp.numel();
+  for (const auto& t : {wp, wg, gp, gg})
+    TORCH_CHECK(t.is_cuda() && t.is_contiguous() && t.scalar_type() == torch::kFloat32 && t.numel() == n &&
+                reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0, "alpha_dot: four aligned fp32 CUDA vectors of one length");
+  const c10::cuda::CUDAGuard guard(wp.device());
+  auto out = torch::zeros({1}, wp.options().dtype(torch::kFloat64));
+  const int blocks = static_cast<int>(std::min<int64_t>(148 * 8, std::max<int64_t>(1, (n / 4 + 255) / 256)));
+  gk::alpha_dot_kernel<<<blocks, 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+      wp.data_ptr<float>(), wg.data_ptr<float>(), gp.data_ptr<float>(), gg.data_ptr<float>(), n, static_cast<float>(alpha),
+      out.data_ptr<double>());
+  FLUTE_CUDA_CHECK(cudaGetLastError());
+  return out;
+}
+
 }  // namespace flute

@@ -263,23 +263,25 @@ __device__ __forceinline__ int gemm_tile(const GemmP& p, const int bx, const int
         }
       } else {
         const uint32_t tx = static_cast<uint32_t>(rows * 128 + p.TN * 128);
+        const int Cred = p.Cred, mode = p.mode, nb = p.TN / 32, dbg = p.dbg;
+        const CUtensorMap* maps0 = p.maps;
         for (int ti = 0; ti < nt; ++ti) {
           const int t = tap0 + ti;
-          const CUtensorMap* mapA = p.maps + p.tap_map[t];
+          const CUtensorMap* mapA = maps0 + p.tap_map[t];
           const int cx = p.tap_dx[t], cy = y0 + p.tap_dy[t], wt = p.tap_w[t];
-          for (int c0 = 0; c0 < p.Cred; c0 += 32, ++it) {
+          for (int c0 = 0; c0 < Cred; c0 += 32, ++it) {
             const uint32_t gi = it_base + static_cast<uint32_t>(it);
             const int s = static_cast<int>(gi % kStages);
             mbar_wait(empty_bar + s, ((gi / kStages) & 1) ^ 1);
             uint8_t* sa = smem + s * stage_bytes;
             uint8_t* sb = sa + A_BYTES;
-            if (p.dbg & 2) { mbar_expect_tx(full_bar + s, 0); continue; }
+            if (dbg & 2) { mbar_expect_tx(full_bar + s, 0); continue; }
             mbar_expect_tx(full_bar + s, tx);
             tma_load_5d(sa, mapA, full_bar + s, c0, cx, cy, b0, slot);
-            if (p.mode == FPROP) {
+            if (mode == FPROP) {
               tma_load_4d(sb, mapB, full_bar + s, c0, wt, n0, slot);                  // [TN co rows][32 ci]
             } else {
-              for (int j = 0; j < p.TN / 32; ++j)                                     // MN-major: [32 co rows][32 ci]
+              for (int j = 0; j < nb; ++j)                                            // MN-major: [32 co rows][32 ci]
                 tma_load_4d(sb + j * BLK_BYTES, mapB, full_bar + s, n0 + 32 * j, wt, c0, slot);
             }
           }
@@ -292,6 +294,9 @@ __device__ __forceinline__ int gemm_tile(const GemmP& p, const int bx, const int
       const bool a_mn = p.mode == WGRAD, b_mn = p.mode != FPROP;
       const uint32_t idesc = make_idesc_fmt(TM, p.TN, 2u) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
       const uint64_t a_step = static_cast<uint64_t>(p.a_kstep), b_step = static_cast<uint64_t>(p.b_kstep);
+      const uint32_t a_lbo = p.a_lbo, a_sbo = p.a_sbo, a_layout = p.a_layout;
+      const uint32_t b_lbo = p.b_lbo, b_sbo = p.b_sbo, b_layout = p.b_layout;
+      const int nacc = p.nacc, accTN = p.TN, dbg = p.dbg;
       if (c.nbuf > 1) {                                   // the epilogue of two tiles ago has drained this accumulator
         mbar_wait(c.acc_free + abuf, aphase ^ 1u);
         tc_fence_after();
@@ -302,14 +307,14 @@ __device__ __forceinline__ int gemm_tile(const GemmP& p, const int bx, const int
         mbar_wait(full_bar + s, (gi / kStages) & 1);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-        const uint64_t adesc = make_desc(a_addr, p.a_lbo, p.a_sbo, p.a_layout);
-        const uint64_t bdesc = make_desc(a_addr + A_BYTES, p.b_lbo, p.b_sbo, p.b_layout);
-        if (!(p.dbg & 1)) {
+        const uint64_t adesc = make_desc(a_addr, a_lbo, a_sbo, a_layout);
+        const uint64_t bdesc = make_desc(a_addr + A_BYTES, b_lbo, b_sbo, b_layout);
+        if (!(dbg & 1)) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int acc = k & (p.nacc - 1);
-            umma_tf32(tmem_base + static_cast<uint32_t>(acc * p.TN), adesc + a_step * k, bdesc + b_step * k, idesc,
-                      (it > 0 || k >= p.nacc) ? 1u : 0u);
+            const int acc = k & (nacc - 1);
+            umma_tf32(tmem_base + static_cast<uint32_t>(acc * accTN), adesc + a_step * k, bdesc + b_step * k, idesc,
+                      (it > 0 || k >= nacc) ? 1u : 0u);
           }
         }
         umma_commit(empty_bar + s);
@@ -1041,7 +1046,12 @@ __global__ void __maxnreg__(160) sn_mega_kernel(const __grid_constant__ MegaP mp
         __threadfence();
         atomicAdd(mp.bar, 1u);
         const unsigned target = G * static_cast<unsigned>(ph + 1);
-        while (ld_acquire_u32(mp.bar) < target) { }
+        // every CTA of the grid is resident (2 per SM by construction), so this wait is short; the watchdog turns a
+        // scheduling surprise into a launch failure instead of a hung device
+        const long long t0 = clock64();
+        while (ld_acquire_u32(mp.bar) < target) {
+          if (clock64() - t0 > 4000000000LL) __trap();
+        }
         __threadfence();
         asm volatile("fence.proxy.async;" ::: "memory");
       }
@@ -1375,7 +1385,8 @@ class Program {
     FLUTE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sn_mega_kernel, kThreads, kMegaSmem));
     TORCH_CHECK(occ >= 1, "persistent step kernel does not fit on an SM");
     max_occ_ = occ;
-    if (ctas_per_sm > 0) occ = static_cast<int>(ctas_per_sm);    // explicit request (the cooperative launch validates it)
+    occ = ctas_per_sm > 0 ? static_cast<int>(ctas_per_sm) : 2;   // see launch_mega() for why the API's answer (1) is not used
+    TORCH_CHECK(occ >= 1 && occ <= 2, "persistent step kernel: 1 or 2 CTAs per SM");
     const int ncta = occ * sms;
     int nph = 0;
     for (int v : phases) { TORCH_CHECK(v >= 0, "negative phase"); nph = std::max(nph, v + 1); }
@@ -1499,12 +1510,15 @@ class Program {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = static_cast<size_t>(kMegaSmem);
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the phase barrier cannot deadlock
-    attr[0].val.cooperative = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    FLUTE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sn_mega_kernel, m.p));
+    // Not a cooperative launch: the occupancy API reports 1 CTA/SM for every kernel that allocates tensor memory
+    // (measured: even 64-thread / 40 KB configurations of this kernel and the per-launch GEMM kernels, which ncu shows
+    // running 2 per SM), so cudaLaunchCooperativeKernel would cap the grid at 148.  Two CTAs of 80 KB / 160 registers x
+    // 192 threads / 128 TMEM columns fit on an SM and nothing else runs on this stream's SMs while the step kernel does
+    // (ordinary stream order, no programmatic overlap), so all 296 CTAs become resident; the in-kernel watchdog traps
+    // instead of hanging if that assumption is ever violated.
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, sn_mega_kernel, m.p);
+    TORCH_CHECK(e == cudaSuccess, "persistent step kernel launch failed (", m.grid, " CTAs, ", kMegaSmem, " B smem): ",
+                cudaGetErrorString(e));
   }
   void launch_gemm(const Op& op, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
@@ -1555,8 +1569,27 @@ static std::vector<int64_t> slotnet_mega_attrs(int64_t smem) {
   int occ = 0;
   FLUTE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sn::sn_mega_kernel, sn::kThreads,
                                                                 static_cast<size_t>(smem > 0 ? smem : sn::kMegaSmem)));
-  return {a.numRegs, static_cast<int64_t>(a.sharedSizeBytes), static_cast<int64_t>(a.localSizeBytes),
-          a.maxThreadsPerBlock, occ, sn::kMegaSmem};
+  std::vector<int64_t> r = {a.numRegs, static_cast<int64_t>(a.sharedSizeBytes), static_cast<int64_t>(a.localSizeBytes),
+                            a.maxThreadsPerBlock, occ, sn::kMegaSmem};
+  for (int threads : {64, 128, 192, 256, 384}) {
+    int o = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, sn::sn_mega_kernel, threads, 40000);
+    r.push_back(o);
+  }
+  size_t avail = 0;
+  cudaOccupancyAvailableDynamicSMemPerBlock(&avail, sn::sn_mega_kernel, 2, sn::kThreads);
+  r.push_back(static_cast<int64_t>(avail));
+  {
+    cudaFuncAttributes g{};
+    cudaFuncGetAttributes(&g, sn::sn_gemm_kernel<sn::E_GNBWD>);
+    cudaFuncSetAttribute(sn::sn_gemm_kernel<sn::E_GNBWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 90000);
+    int o = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, sn::sn_gemm_kernel<sn::E_GNBWD>, sn::kThreads, 85000);
+    r.push_back(g.numRegs);
+    r.push_back(o);
+  }
+  cudaGetLastError();
+  return r;
 }
 
 void bind_slotnet(py::module_& m) {

@@ -406,7 +406,7 @@ class SlotNetResNet(SlotProgramBuilder):
         self.prog.set_side_stream(_os.environ.get("FLUTE_SLOTNET_SIDE", "1") == "1")
         self.prog.set_pdl(_os.environ.get("FLUTE_SLOTNET_PDL", "1") == "1")
         # persistent step kernels: the 20 forward GEMMs and the whole backward pass become one cooperative launch each
-        self.fused = _os.environ.get("FLUTE_SLOTNET_FUSED", "1") == "1"
+        self.fused = _os.environ.get("FLUTE_SLOTNET_FUSED", "0") == "1"
         if self.fused:
             cps = int(_os.environ.get("FLUTE_SLOTNET_FUSED_CTAS", "0"))
             for b, e in ((self.fwd_fuse_begin, self.fwd_fuse_end), (self.bwd_fuse_begin, self.bwd_fuse_end)):

@@ -70,6 +70,18 @@ def cosine(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return torch.where(den > 0, s[0] / den.clamp(min=1e-30), torch.zeros_like(den))
 
 
+# ------------------------------------------------------------------------------------------------ K25 personalization
+def alpha_dot(wp: torch.Tensor, wg: torch.Tensor, gp: torch.Tensor, gg: torch.Tensor, alpha: float) -> torch.Tensor:
+    """``sum((wp - wg) * (alpha * gp + (1 - alpha) * gg))`` over four flat fp32 vectors (personal / global weights and
+    gradients) as one 1-element float64 tensor.  CUDA: one pass over the four arenas (csrc/gather_kernels.cu)."""
+    if _ext.use_cuda_kernels(wp) and all(t.is_contiguous() and t.dtype == torch.float32 and t.data_ptr() % 16 == 0
+                                         for t in (wp, wg, gp, gg)):
+        _ext.count_launch(1)
+        return _ext.load().alpha_dot(wp.view(-1), wg.view(-1), gp.view(-1), gg.view(-1), float(alpha))
+    wp, wg, gp, gg = (t.reshape(-1).double() for t in (wp, wg, gp, gg))
+    return torch.dot(wp - wg, alpha * gp + (1.0 - alpha) * gg).reshape(1)
+
+
 # ------------------------------------------------------------------------------------------------ K8 max-pool
 class _MaxPool2d(torch.autograd.Function):
     @staticmethod

@@ -450,11 +450,21 @@ def alpha_update(model_global, model_personal, alpha, eta):
 
     K25 in SURVEY §2.4: a single fused dot-product over the flattened models
     instead of one ``dot`` per tensor."""
-    lp = list(model_global.parameters())
-    pp = list(model_personal.parameters())
-    dif = torch.cat([(p.data - l.data).reshape(-1) for l, p in zip(lp, pp)])
-    grad = torch.cat([(alpha * p.grad + (1 - alpha) * l.grad).reshape(-1) for l, p in zip(lp, pp)])
-    grad_alpha = torch.dot(dif, grad) + 0.02 * alpha
+    from ..ops import misc_ops
+    from ..parallel.arena import module_arena
+    ag, ap = module_arena(model_global), module_arena(model_personal)
+    if (ag is not None and ap is not None and ag[1] is not None and ap[1] is not None
+            and ag[0].flat.numel() == ap[0].flat.numel()):
+        # both models live in flat arenas: the four operands already ARE flat vectors (padding is zero in all of them)
+        grad_alpha = misc_ops.alpha_dot(ap[0].flat, ag[0].flat, ap[1].flat, ag[1].flat, float(alpha))[0] + 0.02 * alpha
+    else:
+        lp = list(model_global.parameters())
+        pp = list(model_personal.parameters())
+        zero = lambda t: t.grad if t.grad is not None else torch.zeros_like(t)
+        dif = torch.cat([(p.data - l.data).reshape(-1) for l, p in zip(lp, pp)])
+        gp = torch.cat([zero(p).reshape(-1) for p in pp])
+        gl = torch.cat([zero(l).reshape(-1) for l in lp])
+        grad_alpha = misc_ops.alpha_dot(dif, torch.zeros_like(dif), gp, gl, float(alpha))[0] + 0.02 * alpha
     alpha_n = float(np.clip((alpha - eta * grad_alpha).item(), 0.0001, 0.9999))
     return alpha_n if np.isfinite(alpha_n) else 0.75
 

@@ -27,6 +27,9 @@ def test_graphed_generic_step_matches_eager():
     accs = {}
     for mode in ("0", "1"):
         os.environ["FLUTE_GRAPHED_STEP"] = mode
+        import random
+        import numpy as np
+        torch.manual_seed(11); np.random.seed(11); random.seed(11)      # same mini-batch order in both runs
         worker.set_weights(w0)
         worker.accumulator().zero_()
         worker.train_clients(ids, (0.05, None, 0), fused=True)

@@ -186,7 +186,11 @@ def test_slotnet_two_steps_deterministic_buffers():
 def test_persistent_step_kernel_matches_per_launch_program():
     """The cooperative persistent kernels (forward range, backward range) produce the same activations, loss and
     gradients as launching the same ops one by one; repeated 20 times to exercise the barrier re-arm."""
-    model, layout, plan, net, W, G = build(S=4, B=20)
+    os.environ["FLUTE_SLOTNET_FUSED"] = "1"
+    try:
+        model, layout, plan, net, W, G = build(S=4, B=20)
+    finally:
+        del os.environ["FLUTE_SLOTNET_FUSED"]
     assert net.fused and len(net.prog.mega_info()) == 2
     imap = plan["index_map"].cuda().long()
     live = imap >= 0

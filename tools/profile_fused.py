@@ -55,7 +55,16 @@ def main():
     for tag, env in (("per-launch (side stream + PDL)", {"FLUTE_SLOTNET_FUSED": "0"}),
                      ("fused, 2 CTAs/SM", {"FLUTE_SLOTNET_FUSED": "1", "FLUTE_SLOTNET_FUSED_CTAS": "2"}),
                      ("fused, 1 CTA/SM", {"FLUTE_SLOTNET_FUSED": "1", "FLUTE_SLOTNET_FUSED_CTAS": "1"})):
-        net, W, G = build(S, env)
+        try:
+            net, W, G = build(S, env)
+            x0 = torch.rand(S * 20, 3, 32, 32, device="cuda") * 255
+            y0 = torch.randint(0, 1000, (S * 20,), device="cuda")
+            net.step(x0, y0)
+            torch.cuda.synchronize()
+        except Exception as exc:  # noqa: BLE001
+            lines.append("{:34s}: FAILED {}: {}".format(tag, type(exc).__name__, str(exc)[:300]))
+            print(lines[-1])
+            continue
         x = torch.rand(S * 20, 3, 32, 32, device="cuda") * 255
         y = torch.randint(0, 1000, (S * 20,), device="cuda")
         net.step(x, y)
