@@ -8,6 +8,13 @@ void fused_client_step(torch::Tensor w, torch::Tensor g, torch::Tensor hyper, to
                        c10::optional<torch::Tensor> prox_mult, c10::optional<torch::Tensor> prox_loss);
 void slot_gather_bcast(torch::Tensor W, torch::Tensor wg_slot, torch::Tensor wg, torch::Tensor map);
 torch::Tensor alpha_dot(torch::Tensor wp, torch::Tensor wg, torch::Tensor gp, torch::Tensor gg, double alpha);
+bool attention_supported(int64_t S, int64_t D);
+std::vector<torch::Tensor> attention_fwd(torch::Tensor q, torch::Tensor k, torch::Tensor v, c10::optional<torch::Tensor> key_bias,
+                                         double scale, double p_drop, torch::Tensor seed);
+std::vector<torch::Tensor> attention_bwd(torch::Tensor q, torch::Tensor k, torch::Tensor v, torch::Tensor o, torch::Tensor lse,
+                                         torch::Tensor d_o, c10::optional<torch::Tensor> key_bias, double scale, double p_drop,
+                                         torch::Tensor seed);
+torch::Tensor attention_dropout_mask(int64_t B, int64_t H, int64_t S, double p_drop, torch::Tensor seed);
 void slot_pg_sqnorm(torch::Tensor W, torch::Tensor wg_slot, torch::Tensor out);
 void slot_gather_fused(torch::Tensor acc_slot, torch::Tensor W, torch::Tensor wg_slot, torch::Tensor coef,
                        c10::optional<torch::Tensor> sig, c10::optional<torch::Tensor> seed);
@@ -105,6 +112,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         pybind11::arg("prox_loss") = pybind11::none());
   m.def("slot_gather_bcast", &flute::slot_gather_bcast);
   m.def("alpha_dot", &flute::alpha_dot);
+  m.def("attention_supported", &flute::attention_supported);
+  m.def("attention_fwd", &flute::attention_fwd);
+  m.def("attention_bwd", &flute::attention_bwd);
+  m.def("attention_dropout_mask", &flute::attention_dropout_mask);
   m.def("slot_pg_sqnorm", &flute::slot_pg_sqnorm);
   m.def("slot_gather_fused", &flute::slot_gather_fused);
   m.def("slot_scatter_acc", &flute::slot_scatter_acc);

@@ -44,6 +44,16 @@ def build_hf_mlm(model_args):
             over = dict(over, **(model_args.get("config_overrides", {}) or {}))
             cfg = AutoConfig.for_model(mtype, **over)
             cfg._attn_implementation = "sdpa"
+            if model_args.get("tcgen05_attention", True):
+                # hand-written flash-style attention (csrc/attention_tc.cu) through transformers' attention registry;
+                # shapes the kernel does not cover (head_dim != 64, S > 512, CPU) fall back to SDPA inside the hook
+                try:
+                    from ..ops.attention_ops import register_hf
+                    cfg._attn_implementation = register_hf()
+                    return AutoModelForMaskedLM.from_config(cfg)
+                except Exception as exc:         # noqa: BLE001 - an incompatible transformers version keeps SDPA
+                    logging.getLogger(__name__).warning("tcgen05 attention hook unavailable (%s); using SDPA", exc)
+                    cfg._attn_implementation = "sdpa"
             return AutoModelForMaskedLM.from_config(cfg)
     raise ValueError("unknown architecture {!r}: give a local model_name_or_path".format(model_args["model_name"]))
 
