@@ -24,6 +24,7 @@ BASELINE_PUBLISHED = {
 TASKS = {
     "cv_resnet_fedcifar100": {
         "metric": HEADLINE_METRIC, "clients_per_round": 10, "dtype": "fp32",
+        "dtype_label": "fp32 storage, tf32 tensor-core math (tcgen05 kind::tf32)",
         "data": "synthetic Fed-CIFAR-100 shape (500 users x 100 x 32x32x3 uint8), random-init weights",
         "config": {"model": "ResNet-18 (GroupNorm 2 ch/group, per-group affine; 1000-way FC like the reference's RESNET), "
                             "11.7M params", "client_batch": 20, "local_steps_per_client": 5, "global_batch": 1000,
@@ -31,12 +32,14 @@ TASKS = {
     },
     "cv_cnn_femnist": {
         "metric": "fl_rounds_per_sec_cnn_femnist", "clients_per_round": 10,
+        "dtype_label": "bf16 autocast (compute_dtype: bf16 of the task config), fp32 master weights / optimizer",
         "data": "synthetic FedEMNIST shape (3400 users x ~100 x 28x28 uint8, 62 classes), random-init weights",
         "config": {"model": "CNN_DropOut (2 conv + 2 FC, 1.2M params)", "client_batch": 20, "global_batch": None,
                    "seq_len": None},
     },
     "nlp_rnn_fedshakespeare": {
         "metric": "fl_rounds_per_sec_rnn_fedshakespeare_quantized_gather", "clients_per_round": 10,
+        "dtype_label": "fp32 (persistent LSTM kernels, fp32 FMA); 8-bit quantised pseudo-gradients on the gather path",
         "data": "synthetic Shakespeare shape (715 users x sequences of 80 tokens, vocab 90), random-init weights",
         "config": {"model": "Embedding(90,8) + 2xLSTM(256) + FC(90), 0.82M params; DGA with 8-bit gradient "
                             "quantization on the gather path", "client_batch": 4, "global_batch": None, "seq_len": 80},
@@ -45,6 +48,7 @@ TASKS = {
     },
     "mlm_bert": {
         "metric": "fl_rounds_per_sec_bert_base_mlm_global_dp", "clients_per_round": 32,
+        "dtype_label": "fp32 master weights; bf16 tensor-core GEMMs and attention (tcgen05 kind::f16), fp32 accumulate",
         "data": "synthetic token blobs (1000 users, max_seq_length 128, vocab 30522), random-init BERT-base",
         "config": {"model": "BERT-base MLM (HF config, 110M params), DGA + global DP", "client_batch": 8,
                    "global_batch": None, "seq_len": 128},

@@ -81,8 +81,8 @@ class GraphedTrainStep:
             return False
         if t.ss_scheduler is not None:        # scheduled sampling draws host-side random numbers every step
             return False
-        from .trainer import _plain_sgd
-        return t.optimizer is None or _plain_sgd(t.optimizer)
+        from .trainer import _fused_adamw, _plain_sgd
+        return t.optimizer is None or _plain_sgd(t.optimizer) or _fused_adamw(t.optimizer)
 
     def _to_static(self, batch, dev):
         static = {}
@@ -100,6 +100,8 @@ class GraphedTrainStep:
         keep = [x.clone() for x in (w.flat, g.flat, stats, loss_sum)]
         mom = getattr(t, "_mom_state", None)
         keep_mom = [x.clone() for x in mom] if mom is not None else None
+        adam = getattr(t, "_adam_state", None)
+        keep_adam = [x.clone() for x in adam] if adam is not None else None
         buffers = [b for b in t.model.buffers()]
         keep_buf = [b.clone() for b in buffers]
         rng = torch.cuda.get_rng_state(dev)
@@ -112,6 +114,9 @@ class GraphedTrainStep:
                     dst.copy_(src)
             for dst, src in zip(buffers, keep_buf):
                 dst.copy_(src)
+            if getattr(t, "_adam_state", None) is not None:
+                for i, dst in enumerate(t._adam_state):
+                    dst.copy_(keep_adam[i]) if keep_adam is not None else dst.zero_()
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))

@@ -194,6 +194,8 @@ def build_schema():
             "optimizer_config": _optimizer_block(lr_required=False),
             "annealing_config": _annealing_block(strict=False),
             "ss_config": dict(required=False, type="dict", allow_unknown=True, nullable=True),
+            # B200: capture the generic client mini-batch step once into a CUDA graph (core/graphed.py)
+            "graphed_step": _opt("boolean"),
         }),
     }
 

@@ -264,6 +264,12 @@ def _plain_sgd(opt) -> bool:
     return type(opt) is torch.optim.SGD and len(opt.param_groups) == 1 and not opt.param_groups[0].get("maximize", False)
 
 
+def _fused_adamw(opt) -> bool:
+    """The framework's own AdamW (HF / reference semantics) with one parameter group: runs as one fused arena kernel."""
+    from ..utils.optimizers import AdamW
+    return type(opt) is AdamW and len(opt.param_groups) == 1
+
+
 class Trainer(TrainerBase):
     """Mini-batch SGD on one client's data (or on server replay data)."""
 
@@ -382,6 +388,12 @@ class Trainer(TrainerBase):
                                             zero_grad=True, first_step=first)
                 if first is not None:
                     first.zero_()
+            elif _fused_adamw(self.optimizer):
+                grp = self.optimizer.param_groups[0]
+                m, v, step = self._adam_arena(w)
+                step.add_(1)
+                arena_ops.fused_client_adamw(w.flat, g.flat, m, v, step, hyper, stats, n_logical=n, betas=grp["betas"],
+                                             eps=grp["eps"], correct_bias=grp.get("correct_bias", True), zero_grad=True)
             else:
                 arena_ops.clip_and_stats(g.flat, hyper, stats, n_logical=n)
                 self.optimizer.step()
@@ -393,6 +405,15 @@ class Trainer(TrainerBase):
         self.accumulate_gradient_power()
         if self.optimizer is not None:
             self.optimizer.step()
+
+    def _adam_arena(self, w):
+        """(m, v, step) flat AdamW state of the parameter arena; zeroed at the start of every client epoch (the client
+        path clears ``optimizer.state`` per client, ref. ``core/client.py:343-347``)."""
+        st = getattr(self, "_adam_state", None)
+        if st is None or st[0].numel() != w.flat.numel() or st[0].device != w.flat.device:
+            st = (torch.zeros_like(w.flat), torch.zeros_like(w.flat), torch.zeros(1, dtype=torch.int32, device=w.flat.device))
+            self._adam_state = st
+        return st
 
     def _momentum_arena(self, w):
         st = getattr(self, "_mom_state", None)
@@ -439,6 +460,9 @@ class Trainer(TrainerBase):
         self.device_state()[2].zero_()
         if getattr(self, "_mom_state", None) is not None:
             self._mom_state[1].fill_(1)
+        if getattr(self, "_adam_state", None) is not None:
+            for t in self._adam_state:
+                t.zero_()
 
     def _end_epoch(self):
         if self.lr_scheduler is not None:

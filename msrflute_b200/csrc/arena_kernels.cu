@@ -161,6 +161,53 @@ row_update_kernel(float* __restrict__ w, float* __restrict__ g, float* __restric
   }
 }
 
+// AdamW (HF / reference semantics, msrflute_b200/utils/optimizers AdamW == /root/reference/utils/optimizers/adamW.py):
+//   g <- clip(g);  m <- b1 m + (1-b1) g;  v <- b2 v + (1-b2) g^2;  w <- w - lr * bias_corr * m / (sqrt(v) + eps);
+//   w <- w * (1 - lr * wd)   (decoupled, after the update).   `step` is the 1-based step count of the row (device int32).
+__global__ void __launch_bounds__(kThreads)
+row_adamw_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t P,
+                 const float2* __restrict__ partial, int nb_reduce, const float* __restrict__ hyper,
+                 float* __restrict__ stats, const int* __restrict__ step, float n_logical, float b1, float b2, float eps,
+                 bool correct_bias, bool zero_grad) {
+  const int s = blockIdx.y;
+  const float2 tot = fold_partials(partial + static_cast<int64_t>(s) * nb_reduce, nb_reduce);
+  const float lr = hyper[s * 4 + 0], max_norm = hyper[s * 4 + 1], wd = hyper[s * 4 + 2];
+  const float norm = sqrtf(tot.y);
+  const float coef = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    stats[s * 4 + 0] += coef * tot.x;
+    stats[s * 4 + 1] += coef * coef * tot.y;
+    stats[s * 4 + 2] += n_logical;
+    stats[s * 4 + 3] = norm;
+  }
+  const float t = static_cast<float>(step[s]);
+  const float step_size = correct_bias ? lr * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t)) : lr;
+  const float decay = wd > 0.f ? 1.f - lr * wd : 1.f;
+  float4* wv = reinterpret_cast<float4*>(w + static_cast<int64_t>(s) * P);
+  float4* gv = reinterpret_cast<float4*>(g + static_cast<int64_t>(s) * P);
+  float4* mv = reinterpret_cast<float4*>(m + static_cast<int64_t>(s) * P);
+  float4* vv = reinterpret_cast<float4*>(v + static_cast<int64_t>(s) * P);
+  const int64_t n4 = P >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float c1 = 1.f - b1, c2 = 1.f - b2;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n4; i += stride) {
+    float4 gg = ld_na(gv + i), ww = ld_na(wv + i), mm = ld_na(mv + i), v2 = ld_na(vv + i);
+    gg.x *= coef; gg.y *= coef; gg.z *= coef; gg.w *= coef;
+    mm.x = fmaf(b1, mm.x, c1 * gg.x); mm.y = fmaf(b1, mm.y, c1 * gg.y); mm.z = fmaf(b1, mm.z, c1 * gg.z); mm.w = fmaf(b1, mm.w, c1 * gg.w);
+    v2.x = fmaf(b2, v2.x, c2 * gg.x * gg.x); v2.y = fmaf(b2, v2.y, c2 * gg.y * gg.y);
+    v2.z = fmaf(b2, v2.z, c2 * gg.z * gg.z); v2.w = fmaf(b2, v2.w, c2 * gg.w * gg.w);
+    ww.x = (ww.x - step_size * mm.x / (sqrtf(v2.x) + eps)) * decay;
+    ww.y = (ww.y - step_size * mm.y / (sqrtf(v2.y) + eps)) * decay;
+    ww.z = (ww.z - step_size * mm.z / (sqrtf(v2.z) + eps)) * decay;
+    ww.w = (ww.w - step_size * mm.w / (sqrtf(v2.w) + eps)) * decay;
+    st_stream(mv + i, mm);
+    st_stream(vv + i, v2);
+    st_stream(wv + i, ww);
+    if (zero_grad) st_stream(gv + i, zero);
+  }
+}
+
 static void check_rows(const torch::Tensor& t, const char* name) {
   TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kFloat32 && t.dim() == 2 && t.is_contiguous(), name,
               " must be a contiguous fp32 CUDA [S, P] tensor");
@@ -208,6 +255,29 @@ void fused_client_step(torch::Tensor w, torch::Tensor g, torch::Tensor hyper, to
         nb, hyper.data_ptr<float>(), stats.data_ptr<float>(), nullptr, static_cast<float>(n_logical), nesterov,
         static_cast<float>(dampening), zero_grad, pref, pmul);
   }
+  FLUTE_CUDA_CHECK(cudaGetLastError());
+}
+
+void fused_client_adamw(torch::Tensor w, torch::Tensor g, torch::Tensor m, torch::Tensor v, torch::Tensor step,
+                        torch::Tensor hyper, torch::Tensor stats, int64_t n_logical, double beta1, double beta2, double eps,
+                        bool correct_bias, bool zero_grad) {
+  check_rows(w, "w"); check_rows(g, "g"); check_rows(m, "m"); check_rows(v, "v");
+  TORCH_CHECK(w.sizes() == g.sizes() && w.sizes() == m.sizes() && w.sizes() == v.sizes(), "w/g/m/v shape mismatch");
+  const int S = static_cast<int>(w.size(0));
+  const int64_t P = w.size(1);
+  TORCH_CHECK(hyper.is_cuda() && hyper.numel() == S * 4 && stats.is_cuda() && stats.numel() == S * 4 && step.is_cuda() &&
+              step.numel() == S && step.scalar_type() == torch::kInt32);
+  const c10::cuda::CUDAGuard guard(w.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int nb = blocks_for(P >> 2);
+  auto partial = torch::empty({S, nb, 2}, w.options());
+  row_reduce_kernel<<<dim3(nb, S), kThreads, 0, stream>>>(g.data_ptr<float>(), P,
+                                                         reinterpret_cast<float2*>(partial.data_ptr<float>()));
+  row_adamw_kernel<<<dim3(nb, S), kThreads, 0, stream>>>(
+      w.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), P,
+      reinterpret_cast<const float2*>(partial.data_ptr<float>()), nb, hyper.data_ptr<float>(), stats.data_ptr<float>(),
+      step.data_ptr<int>(), static_cast<float>(n_logical), static_cast<float>(beta1), static_cast<float>(beta2),
+      static_cast<float>(eps), correct_bias, zero_grad);
   FLUTE_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -21,6 +21,9 @@ void slot_gather_fused(torch::Tensor acc_slot, torch::Tensor W, torch::Tensor wg
 void slot_scatter_acc(torch::Tensor acc, torch::Tensor acc_slot, torch::Tensor map);
 void dead_coord_noise(torch::Tensor acc, torch::Tensor idx, torch::Tensor sig2_sum, int64_t seed);
 void clip_and_stats(torch::Tensor g, torch::Tensor hyper, torch::Tensor stats, int64_t n_logical);
+void fused_client_adamw(torch::Tensor w, torch::Tensor g, torch::Tensor m, torch::Tensor v, torch::Tensor step,
+                        torch::Tensor hyper, torch::Tensor stats, int64_t n_logical, double beta1, double beta2, double eps,
+                        bool correct_bias, bool zero_grad);
 void pseudo_grad(torch::Tensor wg, torch::Tensor wl, torch::Tensor out, c10::optional<torch::Tensor> weight,
                  c10::optional<torch::Tensor> stats);
 void accumulate_pseudo_grad(torch::Tensor acc, torch::Tensor wg, torch::Tensor wl, torch::Tensor weights,
@@ -120,6 +123,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("slot_gather_fused", &flute::slot_gather_fused);
   m.def("slot_scatter_acc", &flute::slot_scatter_acc);
   m.def("dead_coord_noise", &flute::dead_coord_noise);
+  m.def("fused_client_adamw", &flute::fused_client_adamw);
   m.def("clip_and_stats", &flute::clip_and_stats);
   m.def("pseudo_grad", &flute::pseudo_grad);
   m.def("accumulate_pseudo_grad", &flute::accumulate_pseudo_grad);

@@ -49,6 +49,39 @@ def _2d(t: Optional[torch.Tensor]):
 
 
 # --------------------------------------------------------------- client step
+def fused_client_adamw(w, g, m, v, step, hyper, stats, *, n_logical: int, betas=(0.9, 0.999), eps: float = 1e-6,
+                       correct_bias: bool = True, zero_grad: bool = True):
+    """clip → sufficient stats → AdamW (HF / reference semantics: ``eps`` outside the bias correction, decoupled weight
+    decay applied after the update) → zero grad, per arena row.  ``m, v``: ``[S, P]`` moment arenas, ``step``: ``[S]``
+    int32 device tensor holding the 1-based step count of this update, ``hyper``: ``[S, 4]`` (lr, max_norm, wd, -)."""
+    w2, g2, m2, v2 = _2d(w), _2d(g), _2d(m), _2d(v)
+    b1, b2 = float(betas[0]), float(betas[1])
+    if _ext.use_cuda_kernels(w2, g2, hyper, stats):
+        _ext.load().fused_client_adamw(w2, g2, m2, v2, step, hyper, stats, int(n_logical), b1, b2, float(eps),
+                                       bool(correct_bias), bool(zero_grad))
+        _ext.count_launch(2)
+        return
+    sumsq = (g2 * g2).sum(dim=1)
+    ssum = g2.sum(dim=1)
+    norm = sumsq.sqrt()
+    max_norm = hyper[:, H_MAXNORM]
+    coef = torch.where(max_norm > 0, (max_norm / (norm + 1e-6)).clamp(max=1.0), torch.ones_like(norm))
+    stats[:, S_SUM] += coef * ssum
+    stats[:, S_SUMSQ] += coef * coef * sumsq
+    stats[:, S_COUNT] += float(n_logical)
+    stats[:, S_LASTNORM] = norm
+    gg = g2 * coef[:, None]
+    m2.mul_(b1).add_(gg, alpha=1.0 - b1)
+    v2.mul_(b2).addcmul_(gg, gg, value=1.0 - b2)
+    lr, wd = hyper[:, H_LR, None], hyper[:, H_WD, None]
+    t = step.to(torch.float32).view(-1, 1)
+    step_size = lr * (torch.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)) if correct_bias else lr
+    w2.sub_(step_size * m2 / (v2.sqrt() + eps))
+    w2.mul_(torch.where(wd > 0, 1.0 - lr * wd, torch.ones_like(wd)))
+    if zero_grad:
+        _2d(g).zero_()
+
+
 def fused_client_step(w, g, hyper, stats, mom=None, *, n_logical: int, nesterov: bool = False,
                       dampening: float = 0.0, zero_grad: bool = True, first_step=None, prox_ref=None, prox_mult=None,
                       prox_loss=None):

@@ -9,13 +9,17 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import profile, ProfilerActivity
 
-from bench import build_flagship
+from bench import build_flagship, build_job
 
 
 def main():
     rounds = int(os.environ.get("ROUNDS", "3"))
-    job = build_flagship(n_clients_per_round=10, users=500, norm="gn")
-    for _ in range(8):
+    task = os.environ.get("TASK", "cv_resnet_fedcifar100")
+    if task == "cv_resnet_fedcifar100":
+        job = build_flagship(n_clients_per_round=10, users=500, norm="gn")
+    else:
+        job = build_job(task)
+    for _ in range(int(os.environ.get("SETUP", "8"))):
         job.run_round()
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
@@ -24,6 +28,7 @@ def main():
         torch.cuda.synchronize()
     os.makedirs("gpurun_out", exist_ok=True)
     path = "gpurun_out/round_trace.json"
+    tag = "" if task == "cv_resnet_fedcifar100" else "_" + task
     prof.export_chrome_trace(path)
     tr = json.load(open(path))["traceEvents"]
     gpu = [e for e in tr if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
@@ -73,7 +78,7 @@ def main():
         out.append("  {:9.1f} us  {:5d}  {}".format(t / rounds, n // rounds, k))
     txt = "\n".join(out)
     print(txt)
-    open("gpurun_out/round_timeline.txt", "w").write(txt + "\n")
+    open("gpurun_out/round_timeline{}.txt".format(tag), "w").write(txt + "\n")
     os.remove(path)
     from msrflute_b200.utils.async_ckpt import get_checkpointer
     get_checkpointer().close()
