@@ -7,8 +7,9 @@ the prediction from the zero initial state (the hidden sequence starts with h0, 
 OOV id 0 (predictions of id 0 never count as correct unless ``OOV_correct``).
 
 B200-first: the reference's python time loop issues ~8 small kernels per step.  Here the input projection for
-ALL time steps is one GEMM up front (``X·W_ihᵀ``, tcgen05 on GPUs via ``ops.linear``), and the recurrent part per
-step is one GEMM + one fused gate kernel (``ops.rnn_ops.gru_cell``).
+ALL time steps is one GEMM up front (``X·W_ihᵀ``) and the recurrent part per step is one GEMM + one fused gate kernel
+(``ops.rnn_ops.gru_cell``); with GEMM-shaped batches (≥ 256 rows — the task's 2048) both GEMMs, forward and backward,
+run on the hand-written tcgen05 kernel (``ops.linear_ops``, bf16 operands / fp32 accumulate) instead of cuBLAS.
 """
 from typing import Tuple
 
@@ -27,13 +28,24 @@ class GRU2(T.nn.Module):
         self.w_ih = T.nn.Linear(input_size, 3 * hidden_size, input_bias)
         self.w_hh = T.nn.Linear(hidden_size, 3 * hidden_size, hidden_bias)
 
+    #: run the two projections on the hand-written tcgen05 GEMM (bf16 operands, fp32 accumulate) when the problem is
+    #: GEMM-shaped: the reference task trains with 2048-row batches, i.e. [2048 x 512] x [512 x 1536] per time step
+    TC_MIN_ROWS = 256
+
+    def _proj(self, lin, x):
+        if x.is_cuda and x.shape[0] >= self.TC_MIN_ROWS and getattr(self, "tcgen05_linear", True):
+            from ..ops import linear_ops
+            if linear_ops.tc_available(x, lin.weight):
+                return linear_ops.linear(x, lin.weight, lin.bias).to(x.dtype)
+        return lin(x)
+
     def forward(self, input: Tensor) -> Tuple[Tensor, Tensor]:
         B, L, _ = input.shape
-        gi_all = self.w_ih(input)                                  # one GEMM for every time step
+        gi_all = self._proj(self.w_ih, input.reshape(B * L, -1)).view(B, L, -1)   # one GEMM for every time step
         h = input.new_zeros(B, self.hidden_size)
         hs = [h]
         for t in range(L):
-            h = rnn_ops.gru_cell(gi_all[:, t], self.w_hh(h), h)     # fused r/z/n gates + state update
+            h = rnn_ops.gru_cell(gi_all[:, t], self._proj(self.w_hh, h), h)        # fused r/z/n gates + state update
             hs.append(h)
         return T.stack(hs, dim=1), h
 

@@ -95,3 +95,25 @@ def test_batch_norm_train_matches_torch(N, C, H, res, relu):
     for a, e in zip(got, want):
         assert torch.allclose(a, e, atol=2e-4, rtol=2e-4), float((a - e).abs().max())
     assert torch.allclose(rm1, rm2, atol=1e-5) and torch.allclose(rv1, rv2, atol=1e-4, rtol=1e-4)
+
+
+def test_gru_layer_runs_its_gemms_on_the_tcgen05_kernel():
+    """GEMM-shaped GRU batches (the nlg_gru task trains with 2048 rows): both projections go through ops.linear_ops
+    (bf16 operands) — same hidden states / gradients as the fp32 module within bf16 tolerance."""
+    from msrflute_b200.models.gru_lm import GRU2
+    from msrflute_b200.ops import _ext
+    torch.manual_seed(0)
+    g = GRU2(160, 512).cuda()
+    x = torch.randn(512, 6, 160, device="cuda") * 0.5
+    n0 = _ext.LAUNCH_COUNTER["n"]
+    hs, h = g(x)
+    assert _ext.LAUNCH_COUNTER["n"] - n0 >= 7            # 1 input GEMM + 6 recurrent GEMMs (+ gate kernels)
+    loss = (hs * hs).mean()
+    loss.backward()
+    g_tc = g.w_hh.weight.grad.clone()
+    g.zero_grad()
+    g.tcgen05_linear = False
+    hs_ref, _ = g(x)
+    (hs_ref * hs_ref).mean().backward()
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-12))
+    assert rel(hs, hs_ref) < 2e-2 and rel(g_tc, g.w_hh.weight.grad) < 5e-2, (rel(hs, hs_ref), rel(g_tc, g.w_hh.weight.grad))
