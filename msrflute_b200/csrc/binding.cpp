@@ -48,6 +48,7 @@ std::vector<torch::Tensor> group_norm_bwd(torch::Tensor dy, torch::Tensor x, tor
                                           torch::Tensor rstd, c10::optional<torch::Tensor> y, int64_t G, bool relu,
                                           bool per_group_affine, bool has_residual, int64_t sets);
 
+torch::Tensor gemm_bf16_mn(torch::Tensor a, torch::Tensor b, bool a_mn, bool b_mn, bool out_fp32);
 torch::Tensor gemm_bf16_tn(torch::Tensor a, torch::Tensor b, c10::optional<torch::Tensor> bias, bool relu,
                            bool out_fp32);
 
@@ -134,6 +135,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("group_norm_bwd", &flute::group_norm_bwd);
 
   m.def("gemm_bf16_tn", &flute::gemm_bf16_tn);
+  m.def("gemm_bf16_mn", &flute::gemm_bf16_mn);
 
 
   m.def("group_norm_fwd_arena", &flute::group_norm_fwd_arena);

@@ -38,6 +38,19 @@ __host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n) {
          (static_cast<uint32_t>(umma_m >> 4) << 24);
 }
 
+constexpr int kMnBlockBytes = BLOCK_K * 128;      // one MN-major block: 64 reduction rows x 64 bf16
+// MN-major SWIZZLE_128B operand: 64 contiguous M/N elements per 128-byte row, 8 reduction rows per 1024-byte atom
+// (stride byte offset), 64-wide M/N blocks kMnBlockBytes apart (leading byte offset)
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(kMnBlockBytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 struct EpilogueParams {
   void* C;              // [G, M, N] bf16 or fp32, row-major
   const float* bias;    // [N] or nullptr
@@ -45,6 +58,10 @@ struct EpilogueParams {
   long long c_batch_stride;
   int relu;
   int out_fp32;
+  // operand majorness (persistent kernel): 0 = K-major tile (rows = M/N index, 64 reduction elements per 128-byte row);
+  // 1 = MN-major: the tensor is stored [reduction, M or N] (e.g. dY / X / W as they sit in memory for wgrad / dgrad) and
+  // a tile is BLOCK/64 blocks of [64 reduction rows x 64 M/N elements] — no transposed copy is ever made
+  int a_mn, b_mn;
 };
 
 template <int BLOCK_N>
@@ -246,15 +263,28 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const 
           mbar_wait(empty_bar + s, ((kit / S) & 1) ^ 1);
           uint8_t* sa = smem + s * L::kStageBytes;
           mbar_expect_tx(full_bar + s, L::kStageBytes);
-          tma_load_3d(sa, &map_a, full_bar + s, kb * BLOCK_K, m_blk * BLOCK_M, g);
-          tma_load_3d(sa + L::kABytes, &map_b, full_bar + s, kb * BLOCK_K, n_blk * BLOCK_N, g);
+          if (ep.a_mn) {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_3d(sa + j * kMnBlockBytes, &map_a, full_bar + s, m_blk * BLOCK_M + 64 * j, kb * BLOCK_K, g);
+          } else {
+            tma_load_3d(sa, &map_a, full_bar + s, kb * BLOCK_K, m_blk * BLOCK_M, g);
+          }
+          if (ep.b_mn) {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_3d(sa + L::kABytes + j * kMnBlockBytes, &map_b, full_bar + s, n_blk * BLOCK_N + 64 * j, kb * BLOCK_K, g);
+          } else {
+            tma_load_3d(sa + L::kABytes, &map_b, full_bar + s, kb * BLOCK_K, n_blk * BLOCK_N, g);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (single elected lane)
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N) | (ep.a_mn ? (1u << 15) : 0u) | (ep.b_mn ? (1u << 16) : 0u);
+      const uint64_t a_step = ep.a_mn ? 128u : 2u, b_step = ep.b_mn ? 128u : 2u;     // descriptor units (16 B) per UMMA_K
       int kit = 0, t = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
         const int acc = t & 1;
@@ -266,11 +296,11 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const 
           mbar_wait(full_bar + s, (kit / S) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-          const uint64_t adesc = make_smem_desc(a_addr), bdesc = make_smem_desc(a_addr + L::kABytes);
+          const uint64_t adesc = ep.a_mn ? make_smem_desc_mn(a_addr) : make_smem_desc(a_addr);
+          const uint64_t bdesc = ep.b_mn ? make_smem_desc_mn(a_addr + L::kABytes) : make_smem_desc(a_addr + L::kABytes);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_f16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                     (kb | k) != 0 ? 1u : 0u);
+            umma_f16(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(empty_bar + s);
         }
         umma_commit(acc_full + acc);
@@ -368,6 +398,20 @@ static CUtensorMap make_map(const void* ptr, int64_t G, int64_t R, int64_t K, in
   return m;
 }
 
+// 3-D map over a [G, R (reduction), C (M or N)] bf16 row-major tensor consumed MN-major; box = [1, 64 reduction rows, 64]
+static CUtensorMap make_map_mn(const void* ptr, int64_t G, int64_t R, int64_t C, int64_t batch_stride_elems) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(R), static_cast<cuuint64_t>(G)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(batch_stride_elems) * 2};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(BLOCK_K), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TORCH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (MN-major) failed with code ", static_cast<int>(r));
+  return m;
+}
+
 template <int BLOCK_N>
 static void launch(const CUtensorMap& ma, const CUtensorMap& mb, const EpilogueParams& ep, int G, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N>;
@@ -406,6 +450,40 @@ static int g_gemm_impl = 0;
 
 }  // namespace gemm
 
+// C[M, N] = A · Bᵀ with either operand given in its OTHER storage order (2-D, persistent kernel, N > 64):
+//   a_mn: a is stored [K, M] (reduction-major rows, e.g. dY for wgrad);   b_mn: b is stored [K, N] (e.g. W for dgrad).
+// The MN-major UMMA descriptors read those tiles in place, so linear-layer backward passes need no transposed copies.
+torch::Tensor gemm_bf16_mn(torch::Tensor a, torch::Tensor b, bool a_mn, bool b_mn, bool out_fp32) {
+  using namespace gemm;
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.scalar_type() == torch::kBFloat16 && b.scalar_type() == torch::kBFloat16 &&
+              a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous(), "gemm_bf16_mn: 2-D contiguous bf16");
+  const int64_t M = a_mn ? a.size(1) : a.size(0), K = a_mn ? a.size(0) : a.size(1);
+  const int64_t N = b_mn ? b.size(1) : b.size(0);
+  TORCH_CHECK((b_mn ? b.size(0) : b.size(1)) == K, "reduction length mismatch");
+  TORCH_CHECK(N > 64 && a.size(1) % 8 == 0 && b.size(1) % 8 == 0, "gemm_bf16_mn: N > 64 and 16-byte row pitches");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(a.data_ptr()) % 16 == 0 && reinterpret_cast<uintptr_t>(b.data_ptr()) % 16 == 0);
+  const c10::cuda::CUDAGuard guard(a.device());
+  FLUTE_CUDA_CHECK(cudaSetDevice(a.device().index()));       // driver entry points need a current context on this thread
+  auto stream = at::cuda::getCurrentCUDAStream();
+  torch::Tensor c = torch::empty({M, N}, a.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16));
+  if (M == 0) return c;
+  const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const bool can256 = N >= 256 && (m_tiles * ((N + 255) / 256) >= 148 || K >= 2048);
+  const int block_n = can256 ? 256 : 128;
+  CUtensorMap ma = a_mn ? make_map_mn(a.data_ptr(), 1, K, M, K * M) : make_map(a.data_ptr(), 1, M, K, M * K, BLOCK_M);
+  CUtensorMap mb = b_mn ? make_map_mn(b.data_ptr(), 1, K, N, K * N) : make_map(b.data_ptr(), 1, N, K, N * K, block_n);
+  EpilogueParams ep{};
+  ep.C = c.data_ptr();
+  ep.bias = nullptr;
+  ep.M = static_cast<int>(M); ep.N = static_cast<int>(N); ep.K = static_cast<int>(K);
+  ep.c_batch_stride = M * N;
+  ep.relu = 0;
+  ep.out_fp32 = out_fp32 ? 1 : 0;
+  ep.a_mn = a_mn ? 1 : 0; ep.b_mn = b_mn ? 1 : 0;
+  if (block_n == 256) launch_persistent<256>(ma, mb, ep, 1, stream); else launch_persistent<128>(ma, mb, ep, 1, stream);
+  return c;
+}
+
 // a: [M, K] or [G, M, K] bf16 ; b: [N, K] or [G, N, K] bf16 (a 2-D b is shared by all batches) -> C [.., M, N]
 torch::Tensor gemm_bf16_tn(torch::Tensor a, torch::Tensor b, c10::optional<torch::Tensor> bias, bool relu, bool out_fp32) {
   using namespace gemm;
@@ -437,7 +515,7 @@ torch::Tensor gemm_bf16_tn(torch::Tensor a, torch::Tensor b, c10::optional<torch
   const int64_t b_bstride = (b.dim() == 3) ? N * K : 0;
   CUtensorMap ma = make_map(a.data_ptr(), G, M, K, M * K, BLOCK_M);
   CUtensorMap mb = make_map(b.data_ptr(), b.dim() == 3 ? G : 1, N, K, b_bstride == 0 ? N * K : b_bstride, block_n);
-  EpilogueParams ep;
+  EpilogueParams ep{};
   ep.C = c.data_ptr();
   ep.bias = nullptr;
   torch::Tensor bias_f;

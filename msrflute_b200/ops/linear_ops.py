@@ -4,8 +4,11 @@
 TMA + tcgen05 GEMM (``csrc/gemm_tcgen05.cu``).  All three GEMMs of a training step run on it:
 
     forward   Y[M,N]  = X[M,K]  · W[N,K]ᵀ                    (both operands already K-major)
-    dgrad     dX[M,K] = dY[M,N] · (Wᵀ)[K,N]ᵀ                 (needs W transposed: one small copy)
-    wgrad     dW[N,K] = (dYᵀ)[N,M] · (Xᵀ)[K,M]ᵀ              (needs both activations transposed)
+    dgrad     dX[M,K] = dY[M,N] · W[N,K]                     (W is reduction-major here: MN-major B operand)
+    wgrad     dW[N,K] = dY[M,N]ᵀ · X[M,K]                    (both reduction-major: MN-major A and B operands)
+
+The backward GEMMs read dY, X and W exactly as they sit in memory through MN-major UMMA descriptors
+(``gemm_bf16_mn``) — no ``.t().contiguous()`` copies (three HBM round trips per layer per step in round 1).
 
 Bias add (and an optional ReLU) are fused in the GEMM epilogue.  ``TCLinear`` is a drop-in ``nn.Linear`` replacement
 and ``swap_linear_modules`` retrofits an existing model (e.g. a HuggingFace encoder).  Off-GPU, or for shapes TMA
@@ -21,6 +24,18 @@ def _gemm(a, b, bias=None, relu=False, out_fp32=False):
     out = _ext.load().gemm_bf16_tn(a, b, bias, relu, out_fp32)
     _ext.count_launch(1)
     return out
+
+
+def _gemm_mn(a, b, a_mn, b_mn, out_fp32=False):
+    out = _ext.load().gemm_bf16_mn(a, b, bool(a_mn), bool(b_mn), bool(out_fp32))
+    _ext.count_launch(1)
+    return out
+
+
+def _mn_available():
+    import os
+    ext = _ext.load()
+    return ext is not None and hasattr(ext, "gemm_bf16_mn") and os.environ.get("FLUTE_GEMM_MN", "1") == "1"
 
 
 def tc_available(x, weight):
@@ -51,13 +66,20 @@ class _TCLinearFn(torch.autograd.Function):
         dy2 = dy2.contiguous()
         dx = dw = db = None
         M, K = x2.shape
+        mn = _mn_available() and N % 8 == 0 and K % 8 == 0
         if ctx.needs_input_grad[0]:
-            if N % 8 == 0:
+            if mn and K > 64:
+                # dX = dY · W: W [N, K] is stored reduction-major for this product -> MN-major B operand, read in place
+                dx = _gemm_mn(dy2, w16, False, True, out_fp32=False).view(ctx.in_shape)
+            elif N % 8 == 0:
                 dx = _gemm(dy2, w16.t().contiguous(), None, False, out_fp32=False).view(ctx.in_shape)
             else:
                 dx = (dy2 @ w16).view(ctx.in_shape)
         if ctx.needs_input_grad[1]:
-            if M % 8 == 0:
+            if mn and K > 64:
+                # dW = dYᵀ · X: dY [M, N] and X [M, K] are both stored reduction-major -> MN-major A and B, no copies
+                dw = _gemm_mn(dy2, x2, True, True, out_fp32=True).to(ctx.w_dtype)
+            elif M % 8 == 0:
                 dw = _gemm(dy2.t().contiguous(), x2.t().contiguous(), None, False, out_fp32=True).to(ctx.w_dtype)
             else:
                 dw = (dy2.t().float() @ x2.float()).to(ctx.w_dtype)

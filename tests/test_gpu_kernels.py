@@ -624,3 +624,38 @@ def test_max_pool2d_kernel_matches_torch(shape, k, s, p):
     y2.backward(dy)
     assert torch.equal(y, y2)
     assert torch.allclose(x.grad, x2.grad, atol=1e-6), (x.grad - x2.grad).abs().max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(4096, 768, 3072), (512, 3072, 768), (200, 136, 264), (4096, 768, 768)])
+def test_gemm_mn_major_operands_match_matmul(M, N, K):
+    """C = A·Bᵀ with A and/or B handed over in their other storage order (what linear backward passes have)."""
+    from msrflute_b200.ops import _ext
+    C = _ext.load(required=True)
+    torch.manual_seed(0)
+    a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)         # logical A [M, K]
+    b = (torch.randn(N, K, device="cuda") * 0.5).to(torch.bfloat16)         # logical B [N, K]
+    want = a.float() @ b.float().t()
+    at, bt = a.t().contiguous(), b.t().contiguous()                          # stored [K, M] / [K, N]
+    for a_mn, b_mn in ((False, True), (True, False), (True, True)):
+        got = C.gemm_bf16_mn(at if a_mn else a, bt if b_mn else b, a_mn, b_mn, True)
+        err = float((got - want).norm() / want.norm())
+        assert err < 2e-3, (a_mn, b_mn, err)
+
+
+@pytest.mark.gpu
+def test_tc_linear_backward_without_transposes_matches_fp32():
+    from msrflute_b200.ops import linear_ops
+    torch.manual_seed(1)
+    x = (torch.randn(6, 100, 768, device="cuda") * 0.5).requires_grad_(True)
+    w = (torch.randn(3072, 768, device="cuda") * 0.03).requires_grad_(True)
+    b = torch.zeros(3072, device="cuda", requires_grad=True)
+    y = linear_ops.linear(x, w, b)
+    go = torch.randn_like(y.float()) * 0.1
+    y.float().backward(go)
+    g = [t.grad.clone() for t in (x, w, b)]
+    for t in (x, w, b):
+        t.grad = None
+    (torch.nn.functional.linear(x, w, b)).backward(go)
+    rel = lambda a_, b_: float((a_.float() - b_.float()).norm() / b_.float().norm())
+    assert rel(g[0], x.grad) < 2e-2 and rel(g[1], w.grad) < 2e-2 and rel(g[2], b.grad) < 2e-2
