@@ -13,6 +13,7 @@ the architecture named by ``model_name`` is instantiated from its config with ra
 "random-init weights of that architecture").  Attention runs through PyTorch SDPA (flash kernels on sm_100).
 """
 import logging
+import math
 import os
 
 import torch as T
@@ -93,6 +94,9 @@ class BERT(BaseModel):
         if model_args.get("adapter", False) and hasattr(self.model, "add_adapter"):
             self.model.add_adapter("FLUTE")
             self.model.train_adapter("FLUTE")
+        # fraction of the tokens of a batch that can carry an MLM label (mlm_probability 0.15 + a wide margin); 1.0 = HF's
+        # dense head.  Rows beyond the capacity would be silently ignored, so the margin is ~17 sigma at 4096 tokens.
+        self.mlm_head_rows = float(model_args.get("mlm_head_rows", 0.25))
         self.tc_layers = 0
         if model_args.get("tcgen05_linear", True):
             from ..ops.linear_ops import swap_linear_modules
@@ -123,8 +127,43 @@ class BERT(BaseModel):
     def forward(self, inputs):
         return self.model(**self._prepare_inputs(inputs))
 
+    # ---- masked-rows MLM head ------------------------------------------------------------------------------------------
+    # HF computes vocabulary logits for EVERY position and lets CrossEntropyLoss ignore the ~85 % whose label is -100
+    # (/root/reference/experiments/mlm_bert/model.py:168-189 calls that model as is).  The loss only needs the masked
+    # rows: select them (fixed capacity, so the step stays CUDA-graph capturable), run transform + decoder on those rows
+    # only and feed the fused softmax-CE kernel.  The 768 x 30522 projection — the largest GEMM of the step, forward and
+    # backward — shrinks by ~5x and the [tokens, vocab] fp32 logits are never materialised.
+    def _sparse_head_parts(self):
+        m = self.model
+        enc = getattr(m, "bert", None) or getattr(m, "roberta", None)
+        head = getattr(m, "cls", None) or getattr(m, "lm_head", None)
+        return (enc, head) if enc is not None and head is not None else (None, None)
+
+    def _sparse_mlm_loss(self, inputs):
+        enc, head = self._sparse_head_parts()
+        labels = inputs["labels"]
+        enc_in = {k: v for k, v in inputs.items() if k != "labels"}
+        seq = enc(**enc_in, return_dict=True)[0]
+        n = labels.numel()
+        cap = min(n, max(8, int(math.ceil(self.mlm_head_rows * n))))
+        flat = labels.reshape(-1)
+        valid = flat != -100
+        # rows with a label first (stable), a fixed number of them: no host sync, static shapes
+        order = T.argsort(valid.to(T.int8), descending=True, stable=True)[:cap]
+        rows = seq.reshape(n, seq.shape[-1]).index_select(0, order)
+        lab = flat.index_select(0, order)
+        logits = head(rows)
+        if self.label_smoother is not None:
+            return self.label_smoother({"logits": logits}, lab)
+        from ..ops import misc_ops
+        per_row = misc_ops.softmax_cross_entropy(logits.float(), lab, ignore_index=-100)
+        return per_row.sum() / (lab != -100).sum().clamp(min=1)
+
     def compute_loss(self, inputs, return_outputs=False):
         inputs = self._prepare_inputs(inputs)
+        if (not return_outputs and self.training and self.mlm_head_rows < 1.0 and "labels" in inputs
+                and self._sparse_head_parts()[0] is not None):
+            return self._sparse_mlm_loss(inputs)
         labels = inputs["labels"] if self.label_smoother is not None and "labels" in inputs else None
         outputs = self.model(**inputs)
         loss = self.label_smoother(outputs, labels) if labels is not None else outputs["loss"]

@@ -122,3 +122,35 @@ def test_baseline_config5_bert_mlm_with_global_dp(tmp_path):
                         "max_weight": 1.0, "min_weight": 0.0, "delta": 1e-6, "weight_scaler": 1.0}
     keys = _run_cfg("mlm_bert", cfg, str(tmp_path), "dp")
     assert {"Gradient Norm", "dp_epsilon_rdp", "dp_sigma", "Training loss"} <= keys
+
+
+def test_bert_masked_rows_head_equals_the_dense_hf_loss():
+    """The MLM loss computed from the masked rows only (fixed-capacity selection, fused CE) equals HF's dense
+    logits + CrossEntropyLoss(ignore_index=-100), and so do the gradients."""
+    import torch
+    from msrflute_b200.models.bert_mlm import BERT
+    cfg = {"BERT": {"model": {"model_name": "tiny-bert", "tcgen05_attention": False},
+                    "training": {"seed": 3, "batch_size": 4}}}
+    m = BERT(cfg)
+    m.train()
+    for mod in m.modules():                      # dropout off: the two passes must see the same network
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    torch.manual_seed(0)
+    ids = torch.randint(5, 900, (4, 32))
+    labels = torch.full_like(ids, -100)
+    pick = torch.rand(ids.shape) < 0.15
+    labels[pick] = ids[pick]
+    batch = {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": labels}
+    loss_sparse = m.compute_loss(dict(batch))
+    loss_sparse.backward()
+    g_sparse = [p.grad.clone() for p in m.parameters() if p.grad is not None]
+    m.zero_grad()
+    m.mlm_head_rows = 1.0
+    loss_dense = m.compute_loss(dict(batch))
+    loss_dense.backward()
+    g_dense = [p.grad.clone() for p in m.parameters() if p.grad is not None]
+    assert abs(float(loss_sparse) - float(loss_dense)) < 1e-5
+    assert len(g_sparse) == len(g_dense)
+    for a, b in zip(g_sparse, g_dense):
+        assert torch.allclose(a, b, atol=1e-6, rtol=1e-4)
