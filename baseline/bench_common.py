@@ -64,7 +64,8 @@ TASKS = {
 def parse_args(argv=None):
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--steps", type=int, default=None, help="timed rounds (default: 200 for this repo's flagship — a "
+                   "1.3 s timed region —, 40 for the other tasks, 20 for the reference arm, whose rounds take seconds)")
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--task", default="cv_resnet_fedcifar100", choices=sorted(TASKS))
@@ -75,7 +76,10 @@ def parse_args(argv=None):
     p.add_argument("--clients-per-round", type=int, default=None, help="default: the BASELINE config's value")
     p.add_argument("--sync-ckpt", action="store_true", help="ours only: write latest_model.tar synchronously every "
                    "round like the reference (default: async latest-wins writer)")
-    return p.parse_args(argv)
+    args = p.parse_args(argv)
+    if args.steps is None:
+        args.steps = 20 if args.impl == "reference" else (200 if args.task in ("cv_resnet_fedcifar100", "cv_lr_mnist") else 40)
+    return args
 
 
 class ClockSampler:
