@@ -107,5 +107,10 @@ def make_payload(model, weight):
     ga = grad_arena(model)
     if ga is not None:
         flat = ga.flat.detach().clone()
-        return {"weight": weight, "gradients": ga.layout.views(flat), "flat": flat}
+        pl = {"weight": weight, "gradients": ga.layout.views(flat), "flat": flat}
+        wire = getattr(ga, "quant_wire", None)
+        if wire is not None:                     # quantised payload (DGA): packed wire format between ranks
+            pl["quant"] = wire
+            ga.quant_wire = None
+        return pl
     return {"weight": weight, "gradients": [p.grad.detach().clone() for p in model.parameters()]}

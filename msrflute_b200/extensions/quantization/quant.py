@@ -8,8 +8,9 @@ values with ``|g| <= thresh`` are zeroed.  The reference keeps the result in fp3
 Here the same transform is closed-form (``level = clamp(ceil((g−lo)/w − 1/2), 0, L−1)``; no ``linspace`` /
 ``bucketize`` tables) and runs over the flat gradient arena with a per-tensor segment table; on CUDA it is
 two hand-written kernels (``csrc/misc_kernels.cu``: segmented min/max, then one encode kernel for the whole
-arena) that can ALSO emit the ``quant_bits``-wide level codes + keep mask — the wire format of
-``ops.quant_ops.pack_segments`` / ``unpack_add_``.
+arena).  Between ranks a quantised payload travels PACKED: ``quant_model`` leaves the per-tensor level table on the
+gradient arena, ``make_payload`` attaches it and ``core.federated._send_gradients`` ships ``quant_bits``-wide level codes +
+a 1-bit keep mask + (lo, width) per tensor (``ops.quant_ops.wire_encode`` / ``wire_decode``) instead of fp32 values.
 """
 import logging
 from typing import Optional, Tuple
@@ -49,10 +50,11 @@ def quantize_tensor_(g: torch.Tensor, quant_bits: int, quant_threshold: float, s
     return g
 
 
-def quant_flat_(flat: torch.Tensor, segments, quant_bits: int, quant_threshold: float, global_stats=False):
+def quant_flat_(flat: torch.Tensor, segments, quant_bits: int, quant_threshold: float, global_stats=False,
+                return_stats: bool = False):
     """Quantize a flat gradient buffer in place, tensor by tensor (``segments`` = [(offset, size), …])."""
     from ...ops import quant_ops
-    return quant_ops.quantize_segments_(flat, segments, quant_bits, quant_threshold, global_stats)
+    return quant_ops.quantize_segments_(flat, segments, quant_bits, quant_threshold, global_stats, return_stats=return_stats)
 
 
 def quant_model(model: torch.nn.Module, quant_bits: int = 8, quant_threshold: Optional[float] = None,
@@ -65,8 +67,11 @@ def quant_model(model: torch.nn.Module, quant_bits: int = 8, quant_threshold: Op
     from ...core.strategies.utils import grad_arena
     ga = grad_arena(model)
     if ga is not None:
-        quant_flat_(ga.flat, list(zip(ga.layout.offsets, ga.layout.sizes)), quant_bits, quant_threshold,
-                    global_stats)
+        _, stats = quant_flat_(ga.flat, list(zip(ga.layout.offsets, ga.layout.sizes)), quant_bits, quant_threshold,
+                               global_stats, return_stats=True)
+        # level table of this payload: lets the transport ship level codes + a keep bitmap instead of fp32 values
+        # (ops.quant_ops.wire_encode); consumed (and cleared) by strategies.fedavg.make_payload
+        ga.quant_wire = {"bits": int(quant_bits), "lo_hi": stats[:, :2].detach().clone()} if quant_bits <= 16 else None
         return
     params = [p for p in model.parameters() if p.grad is not None]
     stats = None

@@ -29,10 +29,12 @@ def segment_stats(flat: torch.Tensor, segments, quant_threshold: float, global_s
     return torch.stack([torch.stack(find_min_max_gradient(flat[o:o + n], quant_threshold)) for o, n in segs])
 
 
-def quantize_segments_(flat: torch.Tensor, segments, quant_bits: int, quant_threshold: float, global_stats=False):
+def quantize_segments_(flat: torch.Tensor, segments, quant_bits: int, quant_threshold: float, global_stats=False,
+                       return_stats: bool = False):
     """In-place simulated quantization.  CUDA (``csrc/misc_kernels.cu``): segmented min/max in one pass over the arena
     (ordered-int atomics), |g| quantiles per segment from ``torch.quantile`` (sort-based, exact like the reference),
-    then ONE encode kernel over the whole arena driven by the segment table."""
+    then ONE encode kernel over the whole arena driven by the segment table.  ``return_stats``: also return the
+    ``[n_seg, 3]`` (lo, hi, thresh) table the levels were built from (what :func:`wire_encode` needs)."""
     if _ext.use_cuda_kernels(flat) and not global_stats and flat.is_contiguous() and flat.dtype == torch.float32:
         ext = _ext.load()
         tab = _seg_table(segments, flat.device).contiguous()
@@ -41,13 +43,60 @@ def quantize_segments_(flat: torch.Tensor, segments, quant_bits: int, quant_thre
         stats[:, 2] = torch.stack([_abs_quantile(flat[o:o + n], quant_threshold) for o, n in segs])
         ext.quantize_segments(flat.view(-1), tab, stats, int(quant_bits), False)
         _ext.count_launch(3)
-        return flat
+        return (flat, stats) if return_stats else flat
     from ..extensions.quantization.quant import quantize_tensor_
     stats = segment_stats(flat, segments, quant_threshold, global_stats)
     segs = segments.tolist() if torch.is_tensor(segments) else list(segments)
     for i, (o, n) in enumerate(segs):
         quantize_tensor_(flat[o:o + n], quant_bits, quant_threshold, tuple(stats[i]))
-    return flat
+    return (flat, stats) if return_stats else flat
+
+
+# ------------------------------------------------------------------------------------------------ wire format
+def wire_encode(values: torch.Tensor, sizes, lo_hi: torch.Tensor, quant_bits: int):
+    """Pack an ALREADY quantised dense gradient (``values``: concatenation of tensors of ``sizes`` elements, each
+    snapped to ``2**bits`` levels on its ``[lo, hi]`` or zeroed) into what travels between ranks:
+
+        codes   uint8 level index per element (bits <= 8) or two uint8 byte planes (9..16 bits),
+        bitmap  1 bit per element (1 = the element survived the magnitude threshold),
+        table   float32 [n_seg, 2] = (lo, level width).
+
+    ``4 N`` bytes become ``N + N/8`` (8-bit) or ``2N + N/8`` (9..16-bit).  Decoding reproduces ``lo + code * width``."""
+    assert 1 <= quant_bits <= 16
+    n_bins = 2 ** quant_bits
+    dev = values.device
+    sz = torch.as_tensor(list(sizes), dtype=torch.int64, device=dev)
+    lo = lo_hi[:, 0].to(torch.float32)
+    width = (lo_hi[:, 1].to(torch.float32) - lo) / (n_bins - 1)
+    lo_e = torch.repeat_interleave(lo, sz)
+    w_e = torch.repeat_interleave(torch.where(width > 0, width, torch.ones_like(width)), sz)
+    v = values.reshape(-1).to(torch.float32)
+    idx = torch.round((v - lo_e) / w_e).clamp_(0, n_bins - 1).to(torch.int32)
+    if quant_bits <= 8:
+        codes = idx.to(torch.uint8)
+    else:                                        # two byte planes (every collective backend moves uint8)
+        codes = torch.cat([(idx & 0xFF).to(torch.uint8), (idx >> 8).to(torch.uint8)])
+    keep = v != 0
+    pad = (-keep.numel()) % 8
+    kb = torch.cat([keep, keep.new_zeros(pad)]).view(-1, 8).to(torch.uint8)
+    bitmap = (kb * (2 ** torch.arange(8, device=dev, dtype=torch.uint8))).sum(dim=1).to(torch.uint8)
+    return codes, bitmap, torch.stack([lo, width], dim=1).contiguous()
+
+
+def wire_decode(codes: torch.Tensor, bitmap: torch.Tensor, table: torch.Tensor, sizes) -> torch.Tensor:
+    """Inverse of :func:`wire_encode`: dense fp32 vector."""
+    dev = codes.device
+    sz = torch.as_tensor(list(sizes), dtype=torch.int64, device=dev)
+    total = int(sz.sum())
+    lo_e = torch.repeat_interleave(table[:, 0], sz)
+    w_e = torch.repeat_interleave(table[:, 1], sz)
+    bits = ((bitmap.unsqueeze(1) >> torch.arange(8, device=dev, dtype=torch.uint8)) & 1).bool().view(-1)[:total]
+    if codes.numel() == 2 * total:
+        idx = codes[:total].to(torch.float32) + 256.0 * codes[total:].to(torch.float32)
+    else:
+        idx = codes.to(torch.float32)
+    vals = lo_e + idx * w_e
+    return torch.where(bits, vals, torch.zeros_like(vals))
 
 
 def _abs_quantile(x: torch.Tensor, q: float) -> torch.Tensor:

@@ -217,3 +217,23 @@ def test_multi_rank_variants(tmp_path, name, strategy, server, b200, nproc):
     assert st["i"] == 3
     m = _metrics(exp)
     assert len(m["Training loss"]) == 3 and m["Val loss"][-1] < m["Val loss"][0]
+
+
+def test_quantised_individual_payloads_travel_packed(tmp_path):
+    """DGA with gradient quantisation on the individual-payload path (stale gradients force it), 2 ranks over gloo:
+    worker -> server payloads are level codes + keep bitmap (ops.quant_ops.wire_encode), and the run produces the same
+    model as shipping fp32 values (FLUTE_PACKED_WIRE=0)."""
+    results = {}
+    for mode in ("1", "0"):
+        tmp = str(tmp_path / ("packed" + mode))
+        os.makedirs(tmp)
+        _write_data(tmp)
+        cfgp = _config(tmp, rounds=2, strategy="DGA", extra_server={"aggregate_median": "softmax", "stale_prob": 0.3},
+                       extra_client={"quant_thresh": 0.5, "quant_bits": 8, "quant_anneal": 1.0})
+        exp, log = _run(tmp, cfgp, nproc=2, port=29761 + int(mode), extra_env={"FLUTE_PACKED_WIRE": mode})
+        m = _metrics(exp)
+        results[mode] = (m["Val loss"], log)
+        assert json.load(open(os.path.join(exp, "models", "status_log.json")))["i"] == 2
+    assert "packed messages" in results["1"][1] and "packed messages" not in results["0"][1]
+    for a, b in zip(results["1"][0], results["0"][0]):
+        assert abs(a - b) < 1e-4 * max(1.0, abs(b)), (results["1"][0], results["0"][0])
