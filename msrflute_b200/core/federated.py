@@ -161,6 +161,28 @@ def get_comm() -> Communicator:
     return _Runtime.comm
 
 
+class WorkQueue:
+    """Iterator over the clients THIS rank wins from a job-wide queue (``dispatch: work_queue``).
+
+    Every training rank walks the same cost-sorted list; ``comm.fetch_add`` hands out the next position atomically, so
+    a rank that finishes early simply takes more clients — load balancing by completion, like the reference's
+    acknowledge-and-send-next loop, without a server thread in the middle.  ``taken`` records what this rank trained."""
+
+    def __init__(self, comm, key: str, items: List[int]):
+        self.comm, self.key, self.items, self.taken = comm, key, list(items), []
+
+    def __iter__(self):
+        while True:
+            k = self.comm.fetch_add(self.key, 1)
+            if k >= len(self.items):
+                return
+            self.taken.append(self.items[k])
+            yield self.items[k]
+
+    def __len__(self):
+        return len(self.items)
+
+
 def assign_clients(items: List[int], costs: List[float], workers: List[int], policy: str = "static_lpt",
                    speeds: Optional[dict] = None):
     """Split ``items`` over ``workers``.
@@ -234,13 +256,26 @@ class Server:
         workers = Server._workers(comm)
         costs = costs if costs is not None else [1.0] * len(clients)
         policy = _Runtime.options.get("dispatch", "static_lpt")
+        queue = None
+        if policy == "work_queue":
+            # pull-based dispatch for the per-client (generic) training path; the slot engine consumes whole waves and
+            # evaluation chunks are uniform, so those keep the static plan
+            engine_takes_it = (worker is not None and getattr(worker, "engine", None) is not None and fused
+                               and worker.engine.supports(worker.config))
+            if command == COMMAND_TRAIN and comm.size > 1 and not engine_takes_it and not (defer and fused):
+                order = [c for _, c in sorted(zip(costs, clients), key=lambda t: -t[0])]
+                _Runtime.options["_wq_seq"] = _Runtime.options.get("_wq_seq", 0) + 1
+                queue = {"key": "wq/{}/{}".format(nround, _Runtime.options["_wq_seq"]), "items": order}
+            policy = "static_lpt"
         assign = assign_clients(list(clients), list(costs), workers, policy,
                                 speeds=_Runtime.options.get("_worker_speeds"))
+        if queue is not None:
+            assign = {w: [] for w in workers}
         cost_of = dict(zip(clients, costs))
         flat_ok = torch.is_tensor(weights)
         ctrl = {"cmd": command, "lr": lr, "round": nround, "assign": assign, "mode": mode, "fused": fused,
                 "sync": ("flat" if flat_ok else "list" if weights is not None else "none") if sync_weights else "none",
-                "extra": extra or {}, "defer": bool(defer and fused and command == COMMAND_TRAIN)}
+                "extra": extra or {}, "defer": bool(defer and fused and command == COMMAND_TRAIN), "queue": queue}
         if comm.size > 1:
             comm.bcast_object(ctrl, src=0)
             Server._sync_weights(comm, worker, weights, ctrl["sync"])
@@ -249,8 +284,9 @@ class Server:
 
         # local share
         local_out = []
-        if worker is not None and assign.get(comm.rank if comm.size > 1 else 0):
-            mine = assign[comm.rank if comm.size > 1 else 0]
+        my_rank = comm.rank if comm.size > 1 else 0
+        if worker is not None and (assign.get(my_rank) or (queue is not None and my_rank in workers)):
+            mine = WorkQueue(comm, queue["key"], queue["items"]) if queue is not None else assign[my_rank]
             if command == COMMAND_TRAIN:
                 local_out = worker.train_clients(mine, (lr, None, nround), fused=fused, extra=ctrl["extra"],
                                                  defer=ctrl["defer"])
@@ -551,6 +587,8 @@ class Worker:
             elif ctrl["sync"] == "list":
                 self.set_weights(comm.bcast_object(None, src=0))
             mine = ctrl["assign"].get(comm.rank, [])
+            if ctrl.get("queue") is not None and comm.rank in ctrl["assign"]:
+                mine = WorkQueue(comm, ctrl["queue"]["key"], ctrl["queue"]["items"])
             _maybe_inject_fault(comm.rank, ctrl.get("round", -1))
             if cmd == COMMAND_TRAIN:
                 if ctrl.get("defer"):
@@ -565,6 +603,9 @@ class Worker:
                     continue
                 outs = self.train_clients(mine, (ctrl["lr"], None, ctrl["round"]), fused=ctrl["fused"],
                                           extra=ctrl.get("extra"))
+                if isinstance(mine, WorkQueue):
+                    print_rank("work queue: rank {} trained {} of {} clients of round {}".format(
+                        comm.rank, len(mine.taken), len(mine), ctrl["round"]), logging.INFO)
                 comm.gather_objects([_strip(o) for o in outs])
                 if ctrl["fused"]:
                     comm.reduce_accumulators(self.accumulator(), dst=0)

@@ -84,7 +84,7 @@ B200_KEYS = {
     "device_resident_data": _opt("boolean", default=True),
     "compute_dtype": _opt("string", allowed=["fp32", "bf16"], default="bf16"),
     "server_is_worker": _opt("boolean", default=True),
-    "dispatch": _opt("string", allowed=["static_lpt", "round_robin", "dynamic"], default="static_lpt"),
+    "dispatch": _opt("string", allowed=["static_lpt", "round_robin", "dynamic", "work_queue"], default="static_lpt"),
     "seed": _opt("integer", default=0),
     "async_checkpoint": _opt("boolean"),
     "device_engine": _opt("boolean", default=True),

@@ -76,6 +76,13 @@ class LocalComm(Communicator):
         self.rank, self.size = 0, 1
         self.device = device or (torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available()
                                  else torch.device("cpu"))
+        self._counters = {}
+
+    def fetch_add(self, key: str, n: int = 1) -> int:
+        """Value of the job-wide counter ``key`` before adding ``n`` (the work-queue primitive; trivially local here)."""
+        v = self._counters.get(key, 0)
+        self._counters[key] = v + n
+        return v
 
 
 class CollectiveComm(Communicator):
@@ -93,6 +100,14 @@ class CollectiveComm(Communicator):
         import datetime
         timeout = datetime.timedelta(seconds=float(os.environ.get("FLUTE_COMM_TIMEOUT_S", "1800")))
         self.ctrl_group = dist.new_group(backend="gloo", timeout=timeout) if self.backend != "gloo" else dist.group.WORLD
+
+    def fetch_add(self, key: str, n: int = 1) -> int:
+        """Atomic fetch-and-add on a job-wide counter kept by the rendezvous store (one TCP round trip, no GPU work):
+        the ``work_queue`` dispatch policy pulls client indices from it, so an idle rank takes the next client the
+        moment it finishes one — what the reference does with per-client acknowledgements (``federated.py:344-373``)."""
+        from torch.distributed import distributed_c10d as c10d
+        store = c10d._get_default_store()
+        return int(store.add("flute/" + key, int(n))) - int(n)
 
     def bcast_object(self, obj, src=0):
         box = [obj]

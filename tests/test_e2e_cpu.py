@@ -201,6 +201,9 @@ def test_norm_stats_cosines_fallback_and_server_replay(tmp_path):
 @pytest.mark.parametrize("name,strategy,server,b200,nproc", [
     ("individual_payloads", "DGA", {"aggregate_median": "softmax", "stale_prob": 0.3}, None, 2),   # per-client flat payloads on the wire
     ("reference_layout", "FedAvg", {}, {"server_is_worker": False, "dispatch": "dynamic"}, 3),        # rank 0 = server only
+    ("work_queue", "FedAvg", {}, {"dispatch": "work_queue", "device_engine": False}, 3),               # pull-based dispatch
+    ("work_queue_individual", "DGA", {"aggregate_median": "softmax", "stale_prob": 0.3},
+     {"dispatch": "work_queue", "server_is_worker": False}, 3),
 ])
 def test_multi_rank_variants(tmp_path, name, strategy, server, b200, nproc):
     tmp = str(tmp_path)
@@ -217,6 +220,17 @@ def test_multi_rank_variants(tmp_path, name, strategy, server, b200, nproc):
     assert st["i"] == 3
     m = _metrics(exp)
     assert len(m["Training loss"]) == 3 and m["Val loss"][-1] < m["Val loss"][0]
+    if name.startswith("work_queue"):
+        import re
+        # every client of every round was trained exactly once, by whichever rank pulled it
+        per_round = {}
+        for rank, k, n, rnd in re.findall(r"work queue: rank (\d+) trained (\d+) of (\d+) clients of round (\d+)", log):
+            per_round.setdefault(int(rnd), []).append((int(k), int(n)))
+        own = 0 if (b200 or {}).get("server_is_worker") is False else 1        # rank 0's own share is not logged by Worker.run
+        assert len(per_round) == 3, log[-2000:]
+        for rnd, parts in per_round.items():
+            assert len(parts) == nproc - 1 and all(n == 4 for _, n in parts)
+            assert sum(k for k, _ in parts) <= 4 and (own or sum(k for k, _ in parts) == 4)
 
 
 def test_quantised_individual_payloads_travel_packed(tmp_path):
