@@ -123,3 +123,22 @@ def test_graphed_step_module_is_importable_and_off_by_default():
         assert graphed.enabled({"graphed_step": True}) is False
     finally:
         del os.environ["FLUTE_GRAPHED_STEP"]
+
+
+def test_slotnet_phase_assignment_orders_by_buffer_hazards():
+    """SlotProgramBuilder.phases(): an op's dependency level is one more than the latest earlier op it conflicts with
+    (RAW / WAW / WAR on activation buffers); independent ops share a level (what the persistent step kernel schedules
+    between two grid barriers)."""
+    from msrflute_b200.models.slotnet_resnet import SlotProgramBuilder
+    b = SlotProgramBuilder.__new__(SlotProgramBuilder)
+    X, A1, RES, OUT, DZ = 1, 2, 3, 4, 5
+    b.op_rw = {
+        10: ({X}, {A1}),            # conv1: x -> a1
+        11: ({X}, {RES}),           # downsample: x -> res      (independent of conv1)
+        12: ({A1, RES}, {OUT}),     # conv2 + residual
+        13: ({OUT}, {DZ}),          # next layer
+        14: ({X, DZ}, set()),       # a weight gradient: reads only
+        15: ({DZ}, {X}),            # write-after-read on X: must wait for 10, 11, 14
+    }
+    assert b.phases(10, 16) == [0, 0, 1, 2, 3, 4]
+    assert b.phases(12, 15) == [0, 1, 2]

@@ -38,3 +38,32 @@ def test_quantize_segments_reference_levels_and_sparsity():
         seg = out[o:o + n]
         assert abs((seg == 0).float().mean().item() - 0.5) < 0.01
         assert seg[seg != 0].unique().numel() <= 16
+
+
+def test_attention_ops_cpu_fallback_and_mask_conversion():
+    """ops.attention_ops off the GPU: SDPA fallback with the [B, S, H, D] output contract, key-bias handling, and the
+    compact padding-mask builder registered with transformers."""
+    import torch
+    from msrflute_b200.ops import attention_ops as A
+    torch.manual_seed(0)
+    q, k, v = (torch.randn(2, 3, 10, 16) for _ in range(3))
+    bias = torch.zeros(2, 10)
+    bias[1, 7:] = float("-inf")
+    out = A.attention(q, k, v, key_bias=bias)
+    ref = A.attention_reference(q, k, v, key_bias=bias)
+    assert out.shape == (2, 10, 3, 16) and torch.allclose(out, ref, atol=1e-5)
+    # HF-style masks: a compact [B, 1, 1, S] bool mask becomes a key bias; a materialised [B, 1, S, S] one does not
+    compact = torch.ones(2, 1, 1, 10, dtype=torch.bool)
+    compact[1, :, :, 7:] = False
+    kb, ok = A._key_bias_from_mask(compact, q)
+    assert ok and torch.equal(torch.isinf(kb), ~compact[:, 0, 0, :])
+    assert A._key_bias_from_mask(compact.expand(2, 1, 10, 10).contiguous(), q) == (None, False)
+    assert A._key_bias_from_mask(None, q) == (None, True)
+    o2, w = A.hf_attention_forward(None, q, k, v, compact, dropout=0.0, scaling=0.25)
+    assert w is None and torch.allclose(o2, A.attention_reference(q, k, v, key_bias=bias, scale=0.25), atol=1e-5)
+    from transformers import masking_utils as mu
+    am = torch.ones(2, 10, dtype=torch.long)
+    am[1, 7:] = 0
+    m = A._padding_only_mask(2, 10, 10, mask_function=mu.bidirectional_mask_function, attention_mask=am)
+    assert m.shape == (2, 1, 1, 10) and m.dtype == torch.bool and torch.equal(m[:, 0, 0, :], am.bool())
+    assert A._padding_only_mask(2, 10, 10, mask_function=mu.bidirectional_mask_function, attention_mask=None) is None
