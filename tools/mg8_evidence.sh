@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_multigpu.py -x -q -m gpu 2>&1 | tail -5 > gpurun_out/r2_multigpu_tests_8gpu.log
+FLUTE_MG_FULL=1 timeout 600 python -m pytest tests/test_multigpu.py -x -q -m gpu 2>&1 | tail -5 > gpurun_out/r2_multigpu_tests_8gpu.log
 for N in 8 4 2; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500+N)) bench.py --gpus $N --steps 100 --warmup 5 --no-e2e 2>&1 | tail -1 > gpurun_out/r2_bench_${N}gpu.log
 done
