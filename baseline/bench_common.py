@@ -88,7 +88,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index=0, period_ms=200):
+    def __init__(self, gpu_index=0, period_ms=100):
         self.gpu, self.period = gpu_index, period_ms
         self.proc, self.lines = None, []
 
